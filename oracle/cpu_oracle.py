@@ -1,0 +1,267 @@
+"""CPU oracle for the scoring + calibration + metrics hot path.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs may import it.  Nothing under
+clip_calibration_b200/ imports it and the product path never falls back to it.
+
+It restates, in numpy/scipy/torch-CPU, the algorithm the reference runs for this path.
+Every function cites the reference file:line it follows (paths relative to the reference
+repo root).  Parity of this restatement against the real reference functions is pinned
+by oracle/make_golden.py (run in the build container where /root/reference exists) and
+re-checked by tests/test_oracle_golden.py against the committed fixtures.
+
+Pinned: dac_fit, dac_predict, ece, mce, adaptive_ece, piece, knn_dists (against the
+imported reference functions) and softmax / argmax / confidence (against scipy+numpy as the
+reference calls them).  Parity UNPINNED: the TempScaling *trajectory* (dassl optimiser
+semantics are not in the reference tree); ts_loss_and_grad is pinned to torch autograd only.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+# --------------------------------------------------------------------------------------
+# a-1  logit contraction
+# --------------------------------------------------------------------------------------
+def logits_fp32(img: np.ndarray, txt: np.ndarray, logit_scale: float, threads: int | None = None) -> np.ndarray:
+    """`logits = logit_scale * image_features @ text_features.t()` in fp32 on CPU.
+
+    Python precedence: the scale multiplies the image features first, then the GEMM
+    (trainers/classification/zsclip.py:97-102, trainers/calibration/tempscaling.py:53-56).
+    """
+    import torch
+    if threads is not None:
+        torch.set_num_threads(int(threads))
+    a = torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32))
+    b = torch.from_numpy(np.ascontiguousarray(txt, dtype=np.float32))
+    s = torch.tensor(logit_scale, dtype=torch.float32)
+    return (s * a @ b.t()).numpy()
+
+
+# --------------------------------------------------------------------------------------
+# a-6  DAC fit
+# --------------------------------------------------------------------------------------
+def _knn_sorted(ref_rows: np.ndarray, query: np.ndarray, k: int):
+    # np.linalg.norm(rows - q, axis=1); np.sort(...)[:k]; np.argsort(...)[:k]
+    # (trainers/calibration/distanse_aware_calibration.py:28-30 and :34-36)
+    d = np.linalg.norm(ref_rows - query, axis=1)
+    order = np.argsort(d, kind="stable")[:k]
+    return d[order], order
+
+
+def dac_fit(base_zs, cur_zs, base_tuned, cur_tuned, k: int):
+    """Per-class logit multiplier (trainers/calibration/distanse_aware_calibration.py:13-46).
+
+    Returns (class_confidence[C] float64, knn_idx_zs[C,kk], knn_idx_tuned[C,kk],
+    knn_dist_zs[C,kk], knn_dist_tuned[C,kk]) with kk = min(k, B).  Quirks kept: the mean
+    divides by k even if fewer than k base rows exist (:31, :37); the "< 0.05" base-class
+    test looks at the TUNED nearest distance (:39, variable reused from :35); arithmetic
+    stays in the input dtype.
+    """
+    C = cur_zs.shape[0]
+    B = base_zs.shape[0]
+    kk = min(k, B)
+    cc = []
+    idx_zs = np.zeros((C, kk), np.int64)
+    idx_tu = np.zeros((C, kk), np.int64)
+    d_zs = np.zeros((C, kk), base_zs.dtype)
+    d_tu = np.zeros((C, kk), base_tuned.dtype)
+    for i in range(C):
+        dz, iz = _knn_sorted(base_zs, cur_zs[i], k)
+        zs_score = np.exp(-np.sum(dz) / k)
+        dt, it = _knn_sorted(base_tuned, cur_tuned[i], k)
+        fs_score = np.exp(-np.sum(dt) / k)
+        cc.append(1.0 if dt[0] < 0.05 else fs_score / zs_score)
+        idx_zs[i], idx_tu[i], d_zs[i], d_tu[i] = iz, it, dz, dt
+    return np.array(cc), idx_zs, idx_tu, d_zs, d_tu
+
+
+# --------------------------------------------------------------------------------------
+# a-7  DAC predict on materialised logits
+# --------------------------------------------------------------------------------------
+def dac_predict(logits: np.ndarray, class_confidence: np.ndarray) -> np.ndarray:
+    """fp32: `pred = logits.max(1)[1]; logits *= cc[pred][:, None]`
+    (trainers/calibration/distanse_aware_calibration.py:49-58; CPU statement :62-74).
+    Tie-break: first maximum (numpy argmax)."""
+    x = np.asarray(logits).astype(np.float32)
+    cc = np.asarray(class_confidence).astype(np.float32)
+    pred = np.argmax(x, axis=1)
+    return x * cc[pred][:, None]
+
+
+# --------------------------------------------------------------------------------------
+# a-8 / a-9  softmax, argmax, confidence gather
+# --------------------------------------------------------------------------------------
+def softmax_lastaxis(x: np.ndarray) -> np.ndarray:
+    """scipy.special.softmax(x, axis=-1) as called at trainers/calibration/vl_calibrator.py:91
+    (shift by the row max, exp, divide by the row sum; dtype preserved)."""
+    m = np.max(x, axis=-1, keepdims=True)
+    e = np.exp(x - m)
+    return e / np.sum(e, axis=-1, keepdims=True)
+
+
+def pred_and_conf(probs: np.ndarray):
+    """evaluators/vl_evaluator.py:68 (argmax) and :83 (confidence gather)."""
+    preds = np.argmax(probs, axis=1)
+    confs = probs[np.arange(probs.shape[0]), preds]
+    return preds, confs
+
+
+def score_chain(img, txt, class_confidence, logit_scale: float, chunk: int = 4096, threads=None):
+    """features -> (pred, conf, top-2 logit gap) through the reference composition
+    contraction -> DAC.predict -> softmax -> argmax/gather, row-chunked so that 49k-class
+    vocabularies fit in host memory.  `class_confidence=None` skips DAC (fp32 kept)."""
+    N = img.shape[0]
+    preds = np.empty(N, np.int64)
+    confs = np.empty(N, np.float32)
+    gaps = np.empty(N, np.float32)
+    for lo in range(0, N, chunk):
+        hi = min(N, lo + chunk)
+        lg = logits_fp32(img[lo:hi], txt, logit_scale, threads)
+        if lg.shape[1] > 1:
+            part = np.partition(lg, lg.shape[1] - 2, axis=1)
+            gaps[lo:hi] = part[:, -1] - part[:, -2]
+        else:
+            gaps[lo:hi] = np.inf
+        if class_confidence is not None:
+            lg = dac_predict(lg, class_confidence)
+        p, c = pred_and_conf(softmax_lastaxis(lg))
+        preds[lo:hi], confs[lo:hi] = p, c
+    return preds, confs, gaps
+
+
+# --------------------------------------------------------------------------------------
+# a-10 .. a-12  metrics
+# --------------------------------------------------------------------------------------
+def ece(conf, pred, gt, n_bins: int = 10) -> float:
+    """tools/metrics.py:90-130.  Half-open digitize bins for the means (:104-120), closed
+    last bin from np.histogram for the weights (:127)."""
+    conf, pred, gt = np.asarray(conf), np.asarray(pred), np.asarray(gt)
+    edges = np.linspace(0, 1, n_bins + 1)
+    which = np.digitize(conf, edges) - 1
+    acc = np.zeros(n_bins)
+    mean_conf = np.zeros(n_bins)
+    for b in range(n_bins):
+        sel = which == b
+        if sel.any():
+            acc[b] = np.mean(gt[sel] == pred[sel])
+            mean_conf[b] = np.mean(conf[sel])
+    w = np.histogram(conf, edges)[0] / len(conf)
+    return float(np.sum(w * np.abs(mean_conf - acc)))
+
+
+def _grouped_gap(bin_id, conf, correct):
+    """sum/max building block of MCE / AdaptiveECE / PIECE: per non-empty group
+    |mean(correct) - mean(conf)| * count / N   (tools/metrics.py:203-206, :231-234)."""
+    n = len(conf)
+    out = []
+    for b in np.unique(bin_id):
+        sel = bin_id == b
+        # pandas groupby().mean() Kahan-sums in the column's own dtype and divides by the count
+        # in that dtype; emulated as "correctly rounded sum, then one division" (differs from a
+        # true float32 Kahan loop by at most 1 ulp of the mean, ~6e-8, hence the pin tolerance)
+        ty = conf.dtype.type
+        mean_conf = ty(ty(np.sum(conf[sel].astype(np.float64))) / ty(sel.sum()))
+        out.append(abs(np.mean(correct[sel].astype(np.float64)) - mean_conf) * sel.sum() / n)
+    return np.array(out)
+
+
+def mce(conf, pred, gt, n_bins: int = 10) -> float:
+    """tools/metrics.py:181-208: inner edges only (conf==1.0 falls in the last bin) and the
+    max of the *count-weighted* gaps."""
+    conf, pred, gt = np.asarray(conf), np.asarray(pred), np.asarray(gt)
+    inner = np.linspace(0, 1, n_bins + 1)[1:-1]
+    which = np.digitize(conf, inner)
+    return float(_grouped_gap(which, conf, (pred == gt)).max())
+
+
+def quantile_edges(x: np.ndarray, n_bins: int, method: str = "averaged_inverted_cdf") -> np.ndarray:
+    """Bin edges of sklearn 1.9 KBinsDiscretizer(strategy='quantile') as used at
+    tools/metrics.py:228 (third-party: scikit-learn, unpinned in the reference's
+    requirements; behaviour restated for the installed 1.9.0): percentiles at
+    linspace(0,100,n+1), then edges closer than 1e-8 to their predecessor are dropped.
+    (No subsampling here: sklearn subsamples to 200k rows with an unseeded RNG above that.)"""
+    x = np.asarray(x)                      # percentiles are taken in the column's own dtype
+    q = np.linspace(0, 100, n_bins + 1)
+    edges = np.asarray(np.percentile(x, q, method=method), dtype=np.float64)
+    keep = np.ediff1d(edges, to_begin=np.inf) > 1e-8
+    return edges[keep]
+
+
+def quantile_bin_ids(x: np.ndarray, n_bins: int, method: str = "averaged_inverted_cdf") -> np.ndarray:
+    x = np.asarray(x)
+    if x.min() == x.max():
+        return np.zeros(len(x), np.int64)            # constant feature -> single bin
+    edges = quantile_edges(x, n_bins, method)
+    return np.searchsorted(edges[1:-1], x.astype(np.float64), side="right")
+
+
+def adaptive_ece(conf, pred, gt, n_bins: int = 10, method: str = "averaged_inverted_cdf") -> float:
+    """tools/metrics.py:212-236 (equal-mass bins, sum of count-weighted gaps)."""
+    conf, pred, gt = np.asarray(conf), np.asarray(pred), np.asarray(gt)
+    which = quantile_bin_ids(conf, n_bins, method)
+    return float(_grouped_gap(which, conf, (pred == gt)).sum())
+
+
+def piece(conf, knndist, pred, gt, dist_bin_num: int = 10, conf_bin_num: int = 10,
+          method: str = "averaged_inverted_cdf") -> float:
+    """tools/metrics.py:132-178 with knn_strategy='quantile': 2-D groups
+    (quantile bin of knndist) x (uniform inner-edge bin of conf)."""
+    conf, pred, gt, knndist = map(np.asarray, (conf, pred, gt, knndist))
+    kb = quantile_bin_ids(knndist, dist_bin_num, method)
+    cb = np.digitize(conf, np.linspace(0, 1, conf_bin_num + 1)[1:-1])
+    return float(_grouped_gap(kb * (conf_bin_num + 1) + cb, conf, (pred == gt)).sum())
+
+
+# --------------------------------------------------------------------------------------
+# the (n+1)-bin table the CUDA path emits, restated on CPU (SURVEY.md 8a cross-check)
+# --------------------------------------------------------------------------------------
+FX_SHIFT = 40
+
+
+def bin_table(conf, pred, gt, thresholds) -> np.ndarray:
+    """table[b] = (count, n_correct, sum of round(conf * 2^40)) with b = #(thresholds <= conf)."""
+    conf = np.asarray(conf)
+    thr = np.asarray(thresholds, dtype=np.float64)
+    which = np.searchsorted(thr, conf.astype(np.float64), side="right")
+    correct = (np.asarray(pred) == np.asarray(gt))
+    fx = np.rint(conf.astype(np.float64) * float(1 << FX_SHIFT)).astype(np.uint64)
+    tab = np.zeros((len(thr) + 1, 3), np.uint64)
+    for b in range(len(thr) + 1):
+        sel = which == b
+        tab[b] = (sel.sum(), correct[sel].sum(), fx[sel].sum(dtype=np.uint64))
+    return tab
+
+
+# --------------------------------------------------------------------------------------
+# a-4  temperature-scaling objective
+# --------------------------------------------------------------------------------------
+def ts_loss_and_grad(img, txt, labels, log_scale: float):
+    """loss = F.cross_entropy(exp(t) * img @ txt.T, label) and dloss/dt by autograd
+    (trainers/calibration/tempscaling.py:31-41, :53-56, :155-160), float64 on CPU."""
+    import torch
+    a = torch.from_numpy(np.asarray(img, dtype=np.float64))
+    b = torch.from_numpy(np.asarray(txt, dtype=np.float64))
+    y = torch.from_numpy(np.asarray(labels, dtype=np.int64))
+    t = torch.tensor(float(log_scale), dtype=torch.float64, requires_grad=True)
+    loss = torch.nn.functional.cross_entropy(t.exp() * a @ b.t(), y)
+    loss.backward()
+    return float(loss), float(t.grad)
+
+
+# --------------------------------------------------------------------------------------
+# f-1  image-proximity kNN distances
+# --------------------------------------------------------------------------------------
+def knn_dists(ref_rows, queries, k: int, drop_self: bool = False) -> np.ndarray:
+    """trainers/calibration/proximity.py:19-46 (get_knn_dists) and, with drop_self,
+    :49-70 (get_val_image_knn_dists: k+1 nearest, first dropped), fp32."""
+    import torch
+    r = torch.from_numpy(np.asarray(ref_rows, dtype=np.float32))
+    q = torch.from_numpy(np.asarray(queries, dtype=np.float32))
+    out = []
+    kk = k + 1 if drop_self else k
+    for f in q:
+        d = torch.norm(r - f, dim=1)
+        top, _ = torch.topk(d, k=kk, largest=False)
+        out.append(top[1:].numpy() if drop_self else top.numpy())
+    return np.array(out)

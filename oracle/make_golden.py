@@ -1,0 +1,179 @@
+"""Generate tests/golden/*.npz by running the REAL reference functions (imported from
+/root/reference, which only exists in the build container) on the seeded synthetic cases,
+and pin oracle/cpu_oracle.py against them while doing so.
+
+    python oracle/make_golden.py            # writes tests/golden/, asserts oracle == reference
+
+Reference entry points executed unmodified:
+  trainers/calibration/distanse_aware_calibration.py  DistanseAwareCalibration.fit/.predict
+      (.cuda() patched to identity: the container has no GPU)
+  tools/metrics.py   ECE, MCE, AdaptiveECE, PIECE
+  trainers/calibration/proximity.py   get_knn_dists, get_val_image_knn_dists (.to('cuda') patched)
+and the glue the reference performs inline: `(s*img)@txt.T` in fp32 torch
+(trainers/classification/zsclip.py:97-102), scipy.special.softmax(axis=-1)
+(trainers/calibration/vl_calibrator.py:91), argmax + gather (evaluators/vl_evaluator.py:68,:83).
+"""
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("CCAL_REFERENCE", "/root/reference")
+sys.path.insert(1, REF)
+
+import torch  # noqa: E402
+from scipy.special import softmax  # noqa: E402
+
+torch.Tensor.cuda = lambda self, *a, **k: self          # no GPU in the build container
+_orig_to = torch.Tensor.to
+torch.Tensor.to = lambda self, *a, **k: self if (a and a[0] == "cuda") else _orig_to(self, *a, **k)
+
+import tools.metrics as ref_metrics  # noqa: E402
+from trainers.calibration.distanse_aware_calibration import DistanseAwareCalibration  # noqa: E402
+import trainers.calibration.proximity as ref_prox  # noqa: E402
+
+from clip_calibration_b200 import synth  # noqa: E402
+from oracle import cpu_oracle as orc  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+warnings.filterwarnings("ignore")
+
+
+def ref_chain(case, cc, chunk=4096):
+    N = case.img.shape[0]
+    preds = np.empty(N, np.int64)
+    confs = np.empty(N, np.float32)
+    dac = DistanseAwareCalibration()
+    dac.class_confidence = cc
+    img = torch.from_numpy(case.img)
+    txt = torch.from_numpy(case.txt_tuned)
+    for lo in range(0, N, chunk):
+        hi = min(N, lo + chunk)
+        logits = (torch.tensor(case.logit_scale) * img[lo:hi] @ txt.t()).numpy()
+        # the evaluator round-trips logits through Python floats -> float64 (base_learner.py:94)
+        scaled = dac.predict(logits.astype(np.float64)) if cc is not None else logits
+        probs = softmax(scaled, axis=-1)
+        p = np.argmax(probs, axis=1)
+        preds[lo:hi] = p
+        confs[lo:hi] = probs[np.arange(hi - lo), p]
+    return preds, confs
+
+
+def run_case(name, n_override=None, ks=(5,), fit_classes=None, seed=0):
+    t0 = time.time()
+    case = synth.make_config(name, seed=seed, n_override=n_override)
+    out = {"seed": seed, "N": case.img.shape[0], "C": case.txt_zs.shape[0], "n_base": case.n_base,
+           "signal": case.signal, "logit_scale": case.logit_scale,
+           "img_checksum": float(case.img.astype(np.float64).sum()),
+           "txt_checksum": float(case.txt_tuned.astype(np.float64).sum())}
+    for k in ks:
+        dac = DistanseAwareCalibration()
+        dac.fit(case.base_zs, case.txt_zs, case.base_tuned, case.txt_tuned, k)
+        cc = dac.class_confidence
+        out[f"cc_k{k}"] = cc
+        # pin the oracle's fit (on a class subset when the vocabulary is large)
+        sel = np.arange(len(cc)) if fit_classes is None else np.linspace(0, len(cc) - 1, fit_classes).astype(int)
+        occ, iz, it, dz, dt = orc.dac_fit(case.base_zs, case.txt_zs[sel], case.base_tuned, case.txt_tuned[sel], k)
+        assert np.array_equal(occ, cc[sel]), f"{name}: oracle dac_fit != reference"
+        out[f"fit_sel_k{k}"] = sel
+        out[f"knn_idx_zs_k{k}"] = iz.astype(np.int32)
+        out[f"knn_idx_tuned_k{k}"] = it.astype(np.int32)
+        out[f"knn_dist_tuned_k{k}"] = dt
+    k = ks[len(ks) // 2] if len(ks) > 1 else ks[0]
+    cc = out[f"cc_k{k}"]
+    for tag, ccx in (("dac", cc), ("nodac", None)):
+        pred, conf = ref_chain(case, ccx)
+        opred, oconf, gap = orc.score_chain(case.img, case.txt_tuned, ccx, case.logit_scale)
+        assert np.array_equal(pred, opred), f"{name}/{tag}: oracle pred != reference"
+        assert np.allclose(conf, oconf, rtol=2e-6, atol=0), f"{name}/{tag}: oracle conf != reference"
+        res = {"pred": pred.astype(np.int32), "conf": conf, "gap": gap}
+        for nb in (10, 15):
+            e = ref_metrics.ECE(conf, pred, case.labels, nb)
+            m = ref_metrics.MCE(conf, pred, case.labels, nb)
+            a = ref_metrics.AdaptiveECE(conf, pred, case.labels, nb)
+            assert abs(orc.ece(conf, pred, case.labels, nb) - e) < 1e-12
+            assert abs(orc.mce(conf, pred, case.labels, nb) - m) < 3e-8
+            if len(conf) <= 200000:
+                assert abs(orc.adaptive_ece(conf, pred, case.labels, nb) - a) < 3e-8, (name, tag, nb)
+            res[f"ece{nb}"], res[f"mce{nb}"], res[f"ace{nb}"] = float(e), float(m), float(a)
+        res["acc"] = float(np.mean(pred == case.labels))
+        res["mean_conf"] = float(np.mean(conf))
+        res["counts10"] = np.histogram(conf, np.linspace(0, 1, 11))[0]
+        for kk, v in res.items():
+            out[f"{tag}_{kk}"] = v
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
+    print(f"{name}: N={out['N']} C={out['C']} acc={out['dac_acc']:.6f} ece10={out['dac_ece10']:.8f} "
+          f"mce10={out['dac_mce10']:.8f} ace10={out['dac_ace10']:.8f} nodac_ece10={out['nodac_ece10']:.8f} "
+          f"({time.time()-t0:.1f}s)")
+
+
+def metric_edge_cases():
+    """Small hand-built confidence vectors that hit the binning corner cases
+    (SURVEY.md Appendix A.1-A.3): conf == 1.0, conf exactly on float64 edges, empty bins,
+    float64 confidences, a single sample, all-equal confidences."""
+    rng = np.random.default_rng(7)
+    cases = {}
+    e10 = np.linspace(0, 1, 11)
+    cases["ones_and_half"] = (np.array([1.0, 0.5], np.float32), np.array([0, 0]), np.array([0, 0]))
+    on_edges = np.concatenate([e10.astype(np.float32), np.nextafter(e10.astype(np.float32), np.float32(0)),
+                               np.nextafter(e10.astype(np.float32), np.float32(2))])
+    on_edges = np.clip(on_edges, 0, 1).astype(np.float32)
+    cases["on_edges"] = (on_edges, rng.integers(0, 3, on_edges.size), rng.integers(0, 3, on_edges.size))
+    sat = np.where(rng.random(4000) < 0.4, 1.0, rng.random(4000)).astype(np.float32)
+    cases["saturated"] = (sat, rng.integers(0, 4, 4000), rng.integers(0, 4, 4000))
+    f64 = rng.random(3000)
+    cases["float64_conf"] = (f64, rng.integers(0, 2, 3000), rng.integers(0, 2, 3000))
+    cases["single"] = (np.array([0.3], np.float32), np.array([1]), np.array([1]))
+    narrow = (0.55 + 0.1 * rng.random(2500)).astype(np.float32)
+    cases["narrow"] = (narrow, rng.integers(0, 2, 2500), rng.integers(0, 2, 2500))
+    dup = np.round(rng.random(5000) * 20) / 20
+    cases["many_ties"] = (dup.astype(np.float32), rng.integers(0, 2, 5000), rng.integers(0, 2, 5000))
+    out = {}
+    for name, (conf, pred, gt) in cases.items():
+        out[f"{name}_conf"], out[f"{name}_pred"], out[f"{name}_gt"] = conf, pred.astype(np.int64), gt.astype(np.int64)
+        for nb in (10, 15):
+            e = ref_metrics.ECE(conf, pred, gt, nb)
+            m = ref_metrics.MCE(conf, pred, gt, nb)
+            a = ref_metrics.AdaptiveECE(conf, pred, gt, nb)
+            assert abs(orc.ece(conf, pred, gt, nb) - e) < 1e-12, name
+            assert abs(orc.mce(conf, pred, gt, nb) - m) < 3e-8, name
+            assert abs(orc.adaptive_ece(conf, pred, gt, nb) - a) < 3e-8, (name, nb, orc.adaptive_ece(conf, pred, gt, nb), a)
+            out[f"{name}_ece{nb}"], out[f"{name}_mce{nb}"], out[f"{name}_ace{nb}"] = float(e), float(m), float(a)
+    out["names"] = np.array(sorted(cases))
+    np.savez_compressed(os.path.join(OUT, "metric_edge_cases.npz"), **out)
+    print("metric_edge_cases:", ", ".join(sorted(cases)))
+
+
+def proximity_and_piece():
+    """trainers/calibration/proximity.py + tools/metrics.py PIECE on a small case."""
+    case = synth.make_case("prox", 600, 40, 20, 512, 5, 0.3, seed=3)
+    val = synth.make_case("proxval", 300, 40, 20, 512, 5, 0.3, seed=4).img
+    kd = ref_prox.get_knn_dists(val, case.img, 5)
+    kd_self = ref_prox.get_val_image_knn_dists(val, 5)
+    assert np.allclose(orc.knn_dists(val, case.img, 5), kd, rtol=0, atol=0)
+    assert np.allclose(orc.knn_dists(val, val, 5, drop_self=True), kd_self, rtol=0, atol=0)
+    pred, conf, _ = orc.score_chain(case.img, case.txt_tuned, None, case.logit_scale)
+    prox = np.exp(-np.mean(kd, axis=-1))      # base_learner.py:137
+    out = {"knn": kd, "knn_self": kd_self, "pred": pred, "conf": conf, "labels": case.labels}
+    for nb in (10, 5):
+        p = ref_metrics.PIECE(conf, prox, pred, case.labels, nb, 10)
+        assert abs(orc.piece(conf, prox, pred, case.labels, nb, 10) - p) < 3e-8
+        out[f"piece{nb}"] = float(p)
+    np.savez_compressed(os.path.join(OUT, "proximity_piece.npz"), **out)
+    print("proximity_piece: piece10=%.8f" % out["piece10"])
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    metric_edge_cases()
+    proximity_and_piece()
+    run_case("eurosat")
+    run_case("sun397_l14", ks=(1, 5, 10))
+    run_case("imagenet")
+    run_case("openvocab", n_override=1024, fit_classes=256)
+    print("golden fixtures written to", OUT)
