@@ -1,0 +1,162 @@
+// K3: per-bin {count, n_correct, sum conf} tables for ECE / MCE / ACE / PIECE, and the 16-bit
+// radix histograms that give exact global order statistics (quantile bin edges).
+//
+// HBM-bound streaming kernels: 16 B per image (conf f32 + pred i32 + label i64), read once.
+// Grid = a multiple of the SM count, grid-stride loop, warp-aggregated shared-memory atomics,
+// one set of global atomics per CTA at the end.  Everything is integer / fixed point, so the
+// result does not depend on the grid, the order, or how images are sharded over GPUs.
+#include "ccal_common.cuh"
+
+namespace ccal {
+
+constexpr int kBinThreads = 256;
+
+// small by-value kernel parameter blocks: no device allocation, no extra copies
+struct Thr64 { double t[CCAL_MAX_THRESHOLDS]; };
+struct Thr32 { float t[CCAL_MAX_THRESHOLDS]; };
+struct Prefixes { unsigned int p[64]; };
+
+template <typename ConfT, typename PredT>
+__global__ void __launch_bounds__(kBinThreads)
+bin_stats_kernel(const ConfT* __restrict__ conf, const PredT* __restrict__ pred,
+                 const long long* __restrict__ gt, long long n,
+                 const __grid_constant__ Thr64 thr, int n_thr,
+                 const float* __restrict__ key2, const __grid_constant__ Thr32 thr2, int n_thr2,
+                 unsigned long long* __restrict__ table) {
+  extern __shared__ unsigned char smem_raw[];
+  const int n_cells = (n_thr + 1) * (n_thr2 + 1);
+  BinCell* cells = reinterpret_cast<BinCell*>(smem_raw);
+  double* s_thr = reinterpret_cast<double*>(cells + n_cells);
+  float* s_thr2 = reinterpret_cast<float*>(s_thr + n_thr);
+  for (int i = threadIdx.x; i < n_cells; i += blockDim.x) cells[i] = BinCell{0u, 0u, 0ull};
+  for (int i = threadIdx.x; i < n_thr; i += blockDim.x) s_thr[i] = thr.t[i];
+  for (int i = threadIdx.x; i < n_thr2; i += blockDim.x) s_thr2[i] = thr2.t[i];
+  __syncthreads();
+
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // every lane of a warp runs the same number of iterations (warp_bin_add is warp-collective)
+  const long long n_round = ((n + 31) / 32) * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool valid = i < n;
+    int bin = 0;
+    bool correct = false;
+    unsigned long long fx = 0;
+    if (valid) {
+      const ConfT x = conf[i];
+      const double xd = (double)x;
+      for (int j = 0; j < n_thr; ++j) bin += (xd >= s_thr[j]) ? 1 : 0;
+      if (n_thr2 > 0) bin += bin_of(key2[i], s_thr2, n_thr2) * (n_thr + 1);
+      correct = ((long long)pred[i] == gt[i]);
+      fx = conf_to_fx(x);
+    }
+    warp_bin_add(cells, bin, correct, fx, valid);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_cells; i += blockDim.x) {
+    const BinCell c = cells[i];
+    if (c.count) {
+      atomicAdd(&table[3 * i + 0], (unsigned long long)c.count);
+      atomicAdd(&table[3 * i + 1], (unsigned long long)c.correct);
+      atomicAdd(&table[3 * i + 2], c.sum_fx);
+    }
+  }
+}
+
+// order-preserving key of a non-negative float = its bit pattern
+__global__ void __launch_bounds__(kBinThreads)
+radix_hist_level0(const float* __restrict__ keys, long long n, unsigned int* __restrict__ hist) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned key = __float_as_uint(keys[i]) >> 16;
+    // confidences cluster (e.g. saturated 1.0): one atomic per distinct key per warp
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[key], (unsigned)__popc(peers));
+  }
+}
+
+__global__ void __launch_bounds__(kBinThreads)
+radix_hist_level1(const float* __restrict__ keys, long long n, const __grid_constant__ Prefixes prefixes,
+                  int n_prefix, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int s_pref[64];
+  for (int i = threadIdx.x; i < n_prefix; i += blockDim.x) s_pref[i] = prefixes.p[i];
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned bits = __float_as_uint(keys[i]);
+    const unsigned hi = bits >> 16;
+    for (int p = 0; p < n_prefix; ++p)
+      if (s_pref[p] == hi) atomicAdd(&hist[(size_t)p * 65536u + (bits & 0xFFFFu)], 1u);
+  }
+}
+
+static int grid_for(long long n, int threads, int per_sm) {
+  long long want = (n + threads - 1) / threads;
+  long long cap = (long long)num_sms() * per_sm;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+}  // namespace ccal
+
+using namespace ccal;
+
+extern "C" int ccal_bin_stats(const void* conf, int conf_f64, const void* pred, int pred_i64,
+                              const int64_t* gt, int64_t n, const double* thresholds_host, int n_thr,
+                              const float* key2, const double* thresholds2_host, int n_thr2,
+                              unsigned long long* table, ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE(n >= 0, "ccal_bin_stats: n < 0");
+  CCAL_REQUIRE(n < (1ll << 32), "ccal_bin_stats: n must be < 2^32 per call (32-bit per-CTA counters)");
+  CCAL_REQUIRE(n_thr >= 0 && n_thr <= CCAL_MAX_THRESHOLDS, "ccal_bin_stats: n_thr out of range");
+  CCAL_REQUIRE(n_thr2 >= 0 && n_thr2 <= CCAL_MAX_THRESHOLDS, "ccal_bin_stats: n_thr2 out of range");
+  CCAL_REQUIRE((n_thr + 1) * (n_thr2 + 1) <= 1024, "ccal_bin_stats: more than 1024 cells");
+  CCAL_REQUIRE(table != nullptr, "ccal_bin_stats: table is NULL");
+  CCAL_REQUIRE((n_thr2 == 0) == (key2 == nullptr), "ccal_bin_stats: key2 / n_thr2 mismatch");
+  CCAL_REQUIRE(n_thr == 0 || thresholds_host, "ccal_bin_stats: thresholds NULL");
+  if (n == 0) return CCAL_OK;
+  CCAL_REQUIRE(conf && pred && gt, "ccal_bin_stats: NULL input");
+  CCAL_CUDA_OK(cudaPeekAtLastError());
+
+  Thr64 t1;
+  Thr32 t2;
+  for (int i = 0; i < CCAL_MAX_THRESHOLDS; ++i) {
+    t1.t[i] = i < n_thr ? thresholds_host[i] : 0.0;
+    t2.t[i] = i < n_thr2 ? ceil_to_f32(thresholds2_host[i]) : 0.0f;
+  }
+  const int n_cells = (n_thr + 1) * (n_thr2 + 1);
+  const size_t smem = sizeof(BinCell) * n_cells + sizeof(double) * n_thr + sizeof(float) * n_thr2;
+  const int grid = grid_for(n, kBinThreads, 8);
+  const long long* g = reinterpret_cast<const long long*>(gt);
+#define CCAL_LAUNCH_BIN(CT, PT)                                                                   \
+  bin_stats_kernel<CT, PT><<<grid, kBinThreads, smem, stream>>>(                                  \
+      (const CT*)conf, (const PT*)pred, g, (long long)n, t1, n_thr, key2, t2, n_thr2, table)
+  if (conf_f64) {
+    if (pred_i64) CCAL_LAUNCH_BIN(double, long long); else CCAL_LAUNCH_BIN(double, int);
+  } else {
+    if (pred_i64) CCAL_LAUNCH_BIN(float, long long); else CCAL_LAUNCH_BIN(float, int);
+  }
+#undef CCAL_LAUNCH_BIN
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}
+
+extern "C" int ccal_radix_hist(const float* keys, int64_t n, int level, const uint32_t* prefixes_host,
+                               int n_prefix, uint32_t* hist, ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE(n >= 0 && n < (1ll << 32), "ccal_radix_hist: n out of range");
+  CCAL_REQUIRE(level == 0 || level == 1, "ccal_radix_hist: level must be 0 or 1");
+  CCAL_REQUIRE(hist != nullptr, "ccal_radix_hist: hist is NULL");
+  if (n == 0) return CCAL_OK;
+  CCAL_REQUIRE(keys != nullptr, "ccal_radix_hist: keys is NULL");
+  const int grid = grid_for(n, kBinThreads, 8);
+  if (level == 0) {
+    radix_hist_level0<<<grid, kBinThreads, 0, stream>>>(keys, (long long)n, hist);
+  } else {
+    CCAL_REQUIRE(n_prefix >= 1 && n_prefix <= 64 && prefixes_host, "ccal_radix_hist: 1..64 prefixes required");
+    Prefixes pf;
+    for (int i = 0; i < 64; ++i) pf.p[i] = i < n_prefix ? prefixes_host[i] : 0xFFFFFFFFu;
+    radix_hist_level1<<<grid, kBinThreads, 0, stream>>>(keys, (long long)n, pf, n_prefix, hist);
+  }
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}

@@ -1,0 +1,216 @@
+// K1: exact fp32 k-nearest-rows by Euclidean distance (warp-level top-k) and the DAC map.
+//
+// knn_l2_kernel: CTA = 64 query rows, loops over ALL reference rows in tiles of 64, feature
+// chunks of 16 staged (transposed) in shared memory; each thread owns a 4x4 block of squared
+// distances accumulated as sum (q-r)^2 in fp32 - the reference's own formula
+// (np.linalg.norm(base - cur[i], axis=1)), not 2-2cos, so the "< 0.05" base-class test and
+// the neighbour order do not suffer cancellation.  After a tile, each warp merges the 64 new
+// candidates of its 8 query rows into per-row sorted lists that live in registers, one list
+// entry per lane: an insert is one ballot (rank) + one shuffle (shift).
+// Ties: lower reference index first.
+#include "ccal_common.cuh"
+
+#include <math_constants.h>
+
+namespace ccal {
+
+constexpr int kTile = 64;        // queries per CTA and references per tile
+constexpr int kChunk = 16;       // feature chunk
+constexpr int kPad = 68;         // padded row length of the transposed chunks
+constexpr int kRowsPerWarp = 8;
+constexpr int kMaxList = CCAL_MAX_K + 1;
+
+struct TopList {                 // lane l holds the l-th smallest (d, i) seen so far
+  float d;
+  int i;
+};
+
+__device__ __forceinline__ void list_insert(TopList& e, float d, int i, int cap, int lane) {
+  // rank of the candidate = number of entries ordered before it
+  const bool before = (e.d < d) || (e.d == d && e.i < i);
+  const int pos = __popc(__ballot_sync(0xffffffffu, before && lane < cap));
+  const float up_d = __shfl_up_sync(0xffffffffu, e.d, 1);
+  const int up_i = __shfl_up_sync(0xffffffffu, e.i, 1);
+  if (lane < cap) {
+    if (lane == pos) { e.d = d; e.i = i; }
+    else if (lane > pos) { e.d = up_d; e.i = up_i; }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+knn_l2_kernel(const float* __restrict__ ref, const float* __restrict__ query, long long nr, long long nq,
+              int d, int k, int drop_first, float* __restrict__ dist_out, int* __restrict__ idx_out) {
+  __shared__ __align__(16) float Qs[kChunk][kPad];
+  __shared__ __align__(16) float Rs[kChunk][kPad];
+  __shared__ float Dt[kTile][kTile + 1];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int ty = tid >> 4, tx = tid & 15;           // 16 x 16 threads, 4 x 4 outputs each
+  const int ld_row = tid >> 2, ld_col = (tid & 3) * 4;
+  const long long q0 = (long long)blockIdx.x * kTile;
+  const int cap = min((long long)(k + (drop_first ? 1 : 0)), nr);   // list length actually used
+
+  TopList lists[kRowsPerWarp];
+#pragma unroll
+  for (int r = 0; r < kRowsPerWarp; ++r) lists[r] = TopList{CUDART_INF_F, 0x7fffffff};
+
+  for (long long r0 = 0; r0 < nr; r0 += kTile) {
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+    for (int d0 = 0; d0 < d; d0 += kChunk) {
+      float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), rv = qv;
+      const int dc = d0 + ld_col;
+      if (dc < d) {                                     // d % 4 == 0 is required by the host
+        if (q0 + ld_row < nq) qv = *reinterpret_cast<const float4*>(query + (q0 + ld_row) * d + dc);
+        if (r0 + ld_row < nr) rv = *reinterpret_cast<const float4*>(ref + (r0 + ld_row) * d + dc);
+      }
+      __syncthreads();                                   // previous chunk fully consumed
+      Qs[ld_col + 0][ld_row] = qv.x; Qs[ld_col + 1][ld_row] = qv.y;
+      Qs[ld_col + 2][ld_row] = qv.z; Qs[ld_col + 3][ld_row] = qv.w;
+      Rs[ld_col + 0][ld_row] = rv.x; Rs[ld_col + 1][ld_row] = rv.y;
+      Rs[ld_col + 2][ld_row] = rv.z; Rs[ld_col + 3][ld_row] = rv.w;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < kChunk; ++kk) {
+        const float4 q4 = *reinterpret_cast<const float4*>(&Qs[kk][ty * 4]);
+        const float4 r4 = *reinterpret_cast<const float4*>(&Rs[kk][tx * 4]);
+        const float qa[4] = {q4.x, q4.y, q4.z, q4.w};
+        const float ra[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const float df = ra[b] - qa[a];
+            acc[a][b] = fmaf(df, df, acc[a][b]);
+          }
+      }
+    }
+    // publish the 64 x 64 distances of this tile
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) Dt[ty * 4 + a][tx * 4 + b] = sqrtf(acc[a][b]);
+    __syncthreads();
+
+    // warp-level top-k merge: warp w owns query rows 8w .. 8w+7
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const int row = warp * kRowsPerWarp + r;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int col = lane + 32 * half;
+        const float cand = (r0 + col < nr) ? Dt[row][col] : CUDART_INF_F;
+        float kth = __shfl_sync(0xffffffffu, lists[r].d, cap - 1);
+        unsigned pending = __ballot_sync(0xffffffffu, cand < kth);
+        while (pending) {
+          const int src = __ffs(pending) - 1;
+          pending &= pending - 1;
+          const float cd = __shfl_sync(0xffffffffu, cand, src);
+          if (cd < kth) {                               // warp-uniform
+            list_insert(lists[r], cd, (int)(r0 + 32 * half + src), cap, lane);
+            kth = __shfl_sync(0xffffffffu, lists[r].d, cap - 1);
+          }
+        }
+      }
+    }
+    // Dt is rewritten only after the next tile's chunk loop, which starts with __syncthreads
+  }
+
+  const int skip = drop_first ? 1 : 0;
+#pragma unroll
+  for (int r = 0; r < kRowsPerWarp; ++r) {
+    const long long q = q0 + warp * kRowsPerWarp + r;
+    // entry `lane` of the list goes to output slot lane - skip
+    const int slot = lane - skip;
+    if (q < nq && slot >= 0 && slot < k) {
+      const bool have = lane < cap;
+      if (dist_out) dist_out[q * k + slot] = have ? lists[r].d : CUDART_INF_F;
+      if (idx_out) idx_out[q * k + slot] = have ? lists[r].i : -1;
+    }
+  }
+}
+
+// numpy's float32 add.reduce over a short contiguous vector (pairwise_sum for n < 128)
+__device__ __forceinline__ float numpy_sum_f32(const float* a, int n) {
+  if (n < 8) {
+    float res = 0.f;
+    for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+    return res;
+  }
+  float r[8];
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+  return res;
+}
+
+// class_conf[i] = 1 if nearest tuned distance < 0.05 else exp(-sum(tuned)/k) / exp(-sum(zs)/k)
+__global__ void dac_map_kernel(const float* __restrict__ dist_zs, const float* __restrict__ dist_tuned,
+                               int c, int k, int kk, float* __restrict__ class_conf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  float a[CCAL_MAX_K], b[CCAL_MAX_K];
+  for (int j = 0; j < kk; ++j) { a[j] = dist_zs[(long long)i * k + j]; b[j] = dist_tuned[(long long)i * k + j]; }
+  const float kf = (float)k;                              // divides by k even when kk < k
+  const float zs_score = expf(-__fdiv_rn(numpy_sum_f32(a, kk), kf));
+  const float fs_score = expf(-__fdiv_rn(numpy_sum_f32(b, kk), kf));
+  class_conf[i] = ((double)b[0] < 0.05) ? 1.0f : __fdiv_rn(fs_score, zs_score);
+}
+
+static int launch_knn(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k, int drop_first,
+                      float* dist_out, int32_t* idx_out, cudaStream_t stream) {
+  const long long grid = (nq + kTile - 1) / kTile;
+  CCAL_REQUIRE(grid <= 2147483647ll, "ccal_knn_l2: too many query rows");
+  knn_l2_kernel<<<(int)grid, 256, 0, stream>>>(ref, query, (long long)nr, (long long)nq, d, k, drop_first,
+                                               dist_out, idx_out);
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}
+
+}  // namespace ccal
+
+using namespace ccal;
+
+extern "C" int ccal_knn_l2(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k,
+                           int drop_first, float* dist_out, int32_t* idx_out, ccal_stream_t stream) {
+  CCAL_REQUIRE(nr >= 1 && nq >= 0, "ccal_knn_l2: bad row counts nr=%lld nq=%lld", (long long)nr, (long long)nq);
+  CCAL_REQUIRE(nr < 2147483647ll, "ccal_knn_l2: nr must fit int32");
+  CCAL_REQUIRE(d >= 4 && d % 4 == 0, "ccal_knn_l2: d must be a positive multiple of 4 (got %d)", d);
+  CCAL_REQUIRE(k >= 1 && k <= CCAL_MAX_K, "ccal_knn_l2: k must be in 1..%d (got %d)", CCAL_MAX_K, k);
+  if (nq == 0) return CCAL_OK;
+  CCAL_REQUIRE(ref && query, "ccal_knn_l2: NULL input");
+  CCAL_REQUIRE(((uintptr_t)ref % 16 == 0) && ((uintptr_t)query % 16 == 0), "ccal_knn_l2: 16-byte alignment required");
+  return launch_knn(ref, query, nr, nq, d, k, drop_first, dist_out, idx_out, (cudaStream_t)stream);
+}
+
+extern "C" int ccal_dac_fit(const float* base_zs, const float* cur_zs, const float* base_tuned,
+                            const float* cur_tuned, int b, int c, int d, int k,
+                            float* class_conf_out, int32_t* knn_idx_zs_out, int32_t* knn_idx_tuned_out,
+                            float* knn_dist_zs_out, float* knn_dist_tuned_out, ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE(b >= 1 && c >= 0, "ccal_dac_fit: bad class counts b=%d c=%d", b, c);
+  CCAL_REQUIRE(d >= 4 && d % 4 == 0, "ccal_dac_fit: d must be a positive multiple of 4 (got %d)", d);
+  CCAL_REQUIRE(k >= 1 && k <= CCAL_MAX_K, "ccal_dac_fit: k must be in 1..%d (got %d)", CCAL_MAX_K, k);
+  if (c == 0) return CCAL_OK;
+  CCAL_REQUIRE(base_zs && cur_zs && base_tuned && cur_tuned && class_conf_out, "ccal_dac_fit: NULL input");
+  CCAL_REQUIRE(knn_dist_zs_out && knn_dist_tuned_out,
+               "ccal_dac_fit: the two [c,k] distance buffers are required (they double as workspace)");
+  int rc = launch_knn(base_zs, cur_zs, b, c, d, k, 0, knn_dist_zs_out, knn_idx_zs_out, stream);
+  if (rc) return rc;
+  rc = launch_knn(base_tuned, cur_tuned, b, c, d, k, 0, knn_dist_tuned_out, knn_idx_tuned_out, stream);
+  if (rc) return rc;
+  const int kk = k < b ? k : b;
+  dac_map_kernel<<<(c + 127) / 128, 128, 0, stream>>>(knn_dist_zs_out, knn_dist_tuned_out, c, k, kk, class_conf_out);
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}

@@ -1,0 +1,484 @@
+// K2 / K5: fused scoring on tcgen05 + TMEM + TMA (sm_100a).
+//
+//   logits = s * img @ txt^T  is NEVER written to HBM.  For each 128-row image tile:
+//     pass 1: stream all text tiles (256 classes x 64 features per TMA box), accumulate
+//             128 x 256 fp32 tiles in TMEM, epilogue keeps the running row max / argmax;
+//     pass 2: stream the text tiles again, epilogue accumulates sum_j exp(cc[pred]*(l_j - l_max))
+//             -> confidence = 1 / sum, then bins (confidence, correct) into a shared-memory
+//             histogram (warp-aggregated atomics).
+//   The image tile (128 x D) stays RESIDENT in shared memory for both passes when D <= 512, so
+//   HBM reads every image feature exactly once; the text matrix is re-streamed from L2.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA
+// issuer (one lane), warps 2..5 = epilogue (each owns 32 TMEM lanes = 32 image rows).
+// Pipelines: A slabs (full/empty per 64-feature slab), B ring (full/empty per stage), two TMEM
+// accumulator stages (full/empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// kMode 0 = DAC scoring (ccal_score_fused), kMode 1 = temperature-scaling loss/gradient
+// (ccal_ts_loss_grad: pass 2 also accumulates sum exp*z and picks the label logit).
+#include "ccal_common.cuh"
+#include "sm100_ptx.cuh"
+
+#include <math_constants.h>
+
+namespace ccal {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockN = 256;
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kASlabBytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kBTileBytes = kBlockN * kBlockK * 2;   // 32 KB
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;                       // 2 accumulator stages x 256 fp32 columns
+constexpr int kMaxKBlocks = 16;                      // D <= 1024
+constexpr int kMaxStages = 8;
+constexpr int kCtlBytes = 2048;
+constexpr int kSmemLimit = 232448;                   // 227 KB opt-in maximum per CTA
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct __align__(16) ScoreCtl {                      // head of dynamic shared memory
+  uint64_t a_full[kMaxKBlocks];
+  uint64_t a_empty[kMaxKBlocks];
+  uint64_t b_full[kMaxStages];
+  uint64_t b_empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad_;
+  float thr[CCAL_MAX_THRESHOLDS + 1];
+  BinCell cells[CCAL_MAX_THRESHOLDS + 1];
+};
+static_assert(sizeof(ScoreCtl) <= kCtlBytes, "control block too large");
+
+struct ThrBlock { float t[CCAL_MAX_THRESHOLDS]; };
+
+struct ScoreParams {
+  long long n;
+  int c, d;
+  int kblocks, n_col_tiles, n_row_tiles, stages;
+  uint32_t idesc;
+  float scale;                         // logit_scale (already exponentiated)
+  const float* class_conf;
+  int* pred_out;
+  float* conf_out;
+  float* rowmax_out;
+  const long long* labels;
+  int n_thr;
+  unsigned long long* table;
+  float* row_ws;                       // kMode 1: [2*n] per-row loss / gradient terms
+};
+
+
+// ---- epilogue building blocks: one 32-column chunk of one TMEM lane ----------------------
+// kMasked = the chunk holds fewer than 32 valid classes (last tile of a ragged vocabulary).
+template <bool kMasked>
+__device__ __forceinline__ void max_chunk(const uint32_t (&raw)[32], int nv, int col0, float& m, int& arg) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = (!kMasked || j < nv) ? __uint_as_float(raw[j]) : -CUDART_INF_F;
+  float cm0 = fmaxf(v[0], v[1]), cm1 = fmaxf(v[2], v[3]);
+#pragma unroll
+  for (int j = 4; j < 32; j += 2) { cm0 = fmaxf(cm0, v[j]); cm1 = fmaxf(cm1, v[j + 1]); }
+  const float cm = fmaxf(cm0, cm1);
+  if (cm > m) {                                  // strict: earlier columns win ties (first max)
+    int first = 31;
+#pragma unroll
+    for (int j = 30; j >= 0; --j) first = (v[j] == cm) ? j : first;
+    m = cm;
+    arg = col0 + first;
+  }
+}
+
+template <bool kMasked, int kMode>
+__device__ __forceinline__ void exp_chunk(const uint32_t (&raw)[32], int nv, float a2, float b2, float& sum,
+                                          float& wsum) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, w0 = 0.f, w1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      e[u] = ptx::ex2_approx(fmaf(__uint_as_float(raw[j + u]), a2, -b2));
+      if (kMasked && j + u >= nv) e[u] = 0.f;
+    }
+    s0 += e[0]; s1 += e[1]; s2 += e[2]; s3 += e[3];
+    if (kMode == 1) {
+      w0 = fmaf(e[0], __uint_as_float(raw[j + 0]), w0); w1 = fmaf(e[1], __uint_as_float(raw[j + 1]), w1);
+      w0 = fmaf(e[2], __uint_as_float(raw[j + 2]), w0); w1 = fmaf(e[3], __uint_as_float(raw[j + 3]), w1);
+    }
+  }
+  // chunk partial first, then into the running total: two-level summation keeps the
+  // rounding error of a 49k-term sum at the ~1e-6 level
+  sum += (s0 + s1) + (s2 + s3);
+  if (kMode == 1) wsum += w0 + w1;
+}
+
+template <bool kResident, int kMode>
+__global__ void __launch_bounds__(kThreads, 1)
+score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__ CUtensorMap map_txt,
+                   const __grid_constant__ ScoreParams p, const __grid_constant__ ThrBlock thr) {
+  extern __shared__ unsigned char smem_dyn[];
+  ScoreCtl* ctl = reinterpret_cast<ScoreCtl*>(smem_dyn);
+  // operand area starts at the next 1024-byte boundary (128B-swizzle atoms are 1024 B)
+  const uint32_t ctl_end = ptx::smem_u32(smem_dyn) + kCtlBytes;
+  const uint32_t op_base = (ctl_end + 1023u) & ~1023u;
+  unsigned char* op_ptr = smem_dyn + (op_base - ptx::smem_u32(smem_dyn));
+  // resident: [A slab 0..kblocks) then ring of B tiles; streaming: ring of {A slab, B tile}
+  const uint32_t stage_bytes = kResident ? kBTileBytes : (kASlabBytes + kBTileBytes);
+  unsigned char* ring_ptr = op_ptr + (kResident ? p.kblocks * kASlabBytes : 0);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ------------------------------------------------------------------ one-time setup
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_img);
+    ptx::prefetch_tensormap(&map_txt);
+    for (int i = 0; i < kMaxKBlocks; ++i) { ptx::mbar_init(&ctl->a_full[i], 1); ptx::mbar_init(&ctl->a_empty[i], 1); }
+    for (int i = 0; i < kMaxStages; ++i) { ptx::mbar_init(&ctl->b_full[i], 1); ptx::mbar_init(&ctl->b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&ctl->tmem_full[i], 1); ptx::mbar_init(&ctl->tmem_empty[i], 4); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&ctl->tmem_base, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i <= CCAL_MAX_THRESHOLDS; i += kThreads) {
+    ctl->cells[i] = BinCell{0u, 0u, 0ull};
+    ctl->thr[i] = (i < p.n_thr) ? thr.t[i] : CUDART_INF_F;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  const int NT = p.n_col_tiles;
+  const int KB = p.kblocks;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      uint32_t ti = 0;
+      for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x, ++ti) {
+        const int row0 = tile * kBlockM;
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int nt = 0; nt < NT; ++nt) {
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+              const uint32_t stage = it % (uint32_t)p.stages;
+              const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
+              unsigned char* sp = ring_ptr + (size_t)stage * stage_bytes;
+              if (kResident) {
+                if (pass == 0 && nt == 0) {
+                  // slab kb of the previous row tile must have been consumed by its last MMA
+                  ptx::mbar_wait(&ctl->a_empty[kb], (ti & 1u) ^ 1u);
+                  ptx::mbar_arrive_expect_tx(&ctl->a_full[kb], kASlabBytes);
+                  ptx::tma_load_2d(op_ptr + (size_t)kb * kASlabBytes, &map_img, &ctl->a_full[kb], kb * kBlockK, row0,
+                                   ptx::kEvictFirst);
+                }
+                ptx::mbar_wait(&ctl->b_empty[stage], ph ^ 1u);
+                ptx::mbar_arrive_expect_tx(&ctl->b_full[stage], kBTileBytes);
+                ptx::tma_load_2d(sp, &map_txt, &ctl->b_full[stage], kb * kBlockK, nt * kBlockN, ptx::kEvictLast);
+              } else {
+                ptx::mbar_wait(&ctl->b_empty[stage], ph ^ 1u);
+                ptx::mbar_arrive_expect_tx(&ctl->b_full[stage], kASlabBytes + kBTileBytes);
+                ptx::tma_load_2d(sp, &map_img, &ctl->b_full[stage], kb * kBlockK, row0, ptx::kEvictNormal);
+                ptx::tma_load_2d(sp + kASlabBytes, &map_txt, &ctl->b_full[stage], kb * kBlockK, nt * kBlockN,
+                                 ptx::kEvictLast);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, acc_it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x, ++ti) {
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+            const uint32_t as = acc_it & 1u;
+            const uint32_t aph = (acc_it >> 1) & 1u;
+            ptx::mbar_wait(&ctl->tmem_empty[as], aph ^ 1u);      // epilogue has drained this stage
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * kBlockN;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+              const uint32_t stage = it % (uint32_t)p.stages;
+              const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
+              const uint32_t sp = op_base + (kResident ? (uint32_t)KB * kASlabBytes : 0u) + stage * stage_bytes;
+              if (kResident && pass == 0 && nt == 0) ptx::mbar_wait(&ctl->a_full[kb], ti & 1u);
+              ptx::mbar_wait(&ctl->b_full[stage], ph);
+              ptx::tc_fence_after();
+              const uint32_t a_addr = kResident ? op_base + (uint32_t)kb * kASlabBytes : sp;
+              const uint32_t b_addr = kResident ? sp : sp + kASlabBytes;
+              const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
+              const uint64_t b_desc = ptx::make_kmajor_sw128_desc(b_addr);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                // +32 bytes per 16-element K step inside the 128 B swizzle span (encoded >> 4)
+                ptx::umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc,
+                              (uint32_t)((kb | k) != 0));
+              }
+              ptx::umma_commit(&ctl->b_empty[stage]);             // ring slot reusable when these MMAs retire
+              if (kResident && pass == 1 && nt == NT - 1) ptx::umma_commit(&ctl->a_empty[kb]);
+            }
+            ptx::umma_commit(&ctl->tmem_full[as]);                // accumulator tile complete
+          }
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue (warps 2..5)
+    const int quarter = warp & 3;                                  // TMEM lanes [32q, 32q+32)
+    const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+    uint32_t acc_it = 0;
+    for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x) {
+      const long long row = (long long)tile * kBlockM + quarter * 32 + lane;
+      const bool row_ok = row < p.n;
+      // ---------------- pass 1: running max / first argmax of the raw dot products
+      float m = -CUDART_INF_F;
+      int arg = 0;
+      for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+        const uint32_t as = acc_it & 1u;
+        ptx::mbar_wait(&ctl->tmem_full[as], (acc_it >> 1) & 1u);
+        ptx::tc_fence_after();
+        const int valid = min(kBlockN, p.c - nt * kBlockN);
+        for (int ch = 0; ch * 32 < valid; ++ch) {
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(tmem_base + lane_sel + as * kBlockN + ch * 32, raw);
+          ptx::tmem_ld_wait(raw);
+          const int nv = valid - ch * 32;
+          if (nv >= 32) max_chunk<false>(raw, 32, nt * kBlockN + ch * 32, m, arg);
+          else max_chunk<true>(raw, nv, nt * kBlockN + ch * 32, m, arg);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[as]);
+      }
+      // ---------------- pass 2: sum of exp at the predicted class's multiplier
+      float cc = 1.0f;
+      if (kMode == 0 && p.class_conf != nullptr) cc = __ldg(p.class_conf + arg);
+      const float a2 = cc * p.scale * kLog2e;
+      const float b2 = m * a2;
+      float sum = 0.f, wsum = 0.f, zy = 0.f;
+      const int label = (kMode == 1 && row_ok) ? (int)p.labels[row] : -1;
+      for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+        const uint32_t as = acc_it & 1u;
+        ptx::mbar_wait(&ctl->tmem_full[as], (acc_it >> 1) & 1u);
+        ptx::tc_fence_after();
+        const int valid = min(kBlockN, p.c - nt * kBlockN);
+        for (int ch = 0; ch * 32 < valid; ++ch) {
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(tmem_base + lane_sel + as * kBlockN + ch * 32, raw);
+          ptx::tmem_ld_wait(raw);
+          const int nv = valid - ch * 32;
+          if (nv >= 32) exp_chunk<false, kMode>(raw, 32, a2, b2, sum, wsum);
+          else exp_chunk<true, kMode>(raw, nv, a2, b2, sum, wsum);
+          if (kMode == 1) {
+            const int rel = label - (nt * kBlockN + ch * 32);
+            if (rel >= 0 && rel < 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) zy = (j == rel) ? __uint_as_float(raw[j]) : zy;
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[as]);
+      }
+      // ---------------- per-row results
+      if (kMode == 0) {
+        const float conf = 1.0f / sum;
+        if (row_ok) {
+          if (p.pred_out) p.pred_out[row] = arg;
+          if (p.conf_out) p.conf_out[row] = conf;
+          if (p.rowmax_out) p.rowmax_out[row] = m * p.scale;
+        }
+        if (p.table != nullptr) {
+          const bool correct = row_ok && ((long long)arg == p.labels[row]);
+          warp_bin_add(ctl->cells, bin_of(conf, ctl->thr, p.n_thr), correct, conf_to_fx(conf), row_ok);
+        }
+      } else if (row_ok) {
+        // loss_i = logsumexp_j(s z_j) - s z_y ;  d loss_i / dt = s (sum_j p_j z_j - z_y), s = exp(t)
+        p.row_ws[row] = logf(sum) + p.scale * (m - zy);
+        p.row_ws[p.n + row] = p.scale * (wsum / sum - zy);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+  if (kMode == 0 && p.table != nullptr) {
+    for (int i = threadIdx.x; i <= p.n_thr; i += kThreads) {
+      const BinCell cell = ctl->cells[i];
+      if (cell.count) {
+        atomicAdd(&p.table[3 * i + 0], (unsigned long long)cell.count);
+        atomicAdd(&p.table[3 * i + 1], (unsigned long long)cell.correct);
+        atomicAdd(&p.table[3 * i + 2], cell.sum_fx);
+      }
+    }
+  }
+}
+
+// deterministic fixed-order reduction of the per-row loss / gradient terms (kMode 1)
+__global__ void __launch_bounds__(1024)
+ts_reduce_kernel(const float* __restrict__ row_ws, long long n, double* __restrict__ out2) {
+  __shared__ double s_loss[32], s_grad[32];
+  double loss = 0.0, grad = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    loss += (double)row_ws[i];
+    grad += (double)row_ws[n + i];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    loss += __shfl_xor_sync(0xffffffffu, loss, off);
+    grad += __shfl_xor_sync(0xffffffffu, grad, off);
+  }
+  if ((threadIdx.x & 31) == 0) { s_loss[threadIdx.x >> 5] = loss; s_grad[threadIdx.x >> 5] = grad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double l = 0.0, g = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { l += s_loss[w]; g += s_grad[w]; }
+    out2[0] = l / (double)n;
+    out2[1] = g / (double)n;
+  }
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// [rows, d] row-major 16-bit matrix, box = {64 features, box_rows}, 128-byte swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const void* base, long long rows, int d, int box_rows, int dtype) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(CCAL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dtype == CCAL_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CCAL_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return CCAL_OK;
+}
+
+template <bool kResident, int kMode>
+static int launch_variant(const CUtensorMap& mi, const CUtensorMap& mt, const ScoreParams& p, const ThrBlock& thr,
+                          int grid, size_t smem, cudaStream_t stream) {
+  auto kern = score_fused_kernel<kResident, kMode>;
+  CCAL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kThreads, smem, stream>>>(mi, mt, p, thr);
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}
+
+static int run_fused(int mode, const void* img, const void* txt, int64_t n, int c, int d, int dtype, ScoreParams p,
+                     const ThrBlock& thr, cudaStream_t stream) {
+  int rc = ccal_check_device();
+  if (rc) return rc;
+  CCAL_REQUIRE(n >= 1 && c >= 1, "fused scoring: bad shape n=%lld c=%d", (long long)n, c);
+  CCAL_REQUIRE(d >= 64 && d % 64 == 0 && d <= 64 * kMaxKBlocks,
+               "fused scoring: feature width must be a multiple of 64 in [64, %d] (got %d)", 64 * kMaxKBlocks, d);
+  CCAL_REQUIRE(dtype == CCAL_BF16 || dtype == CCAL_F16, "fused scoring: operands must be bf16 or fp16");
+  CCAL_REQUIRE(img && txt, "fused scoring: NULL feature pointer");
+  CCAL_REQUIRE(((uintptr_t)img % 16 == 0) && ((uintptr_t)txt % 16 == 0), "fused scoring: 16-byte alignment required");
+  CCAL_REQUIRE(n <= 2147483647ll - kBlockM, "fused scoring: n must fit int32 row coordinates");
+
+  CUtensorMap map_img, map_txt;
+  rc = make_map(&map_img, img, n, d, kBlockM, dtype);
+  if (rc) return rc;
+  rc = make_map(&map_txt, txt, c, d, kBlockN, dtype);
+  if (rc) return rc;
+
+  p.n = n; p.c = c; p.d = d;
+  p.kblocks = d / kBlockK;
+  p.n_col_tiles = (c + kBlockN - 1) / kBlockN;
+  p.n_row_tiles = (int)((n + kBlockM - 1) / kBlockM);
+  const uint32_t fmt = (dtype == CCAL_BF16) ? 1u : 0u;
+  // tcgen05 instruction descriptor, kind::f16: D=f32, A/B=fmt, both K-major, N=256, M=128
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+
+  const int avail = kSmemLimit - kCtlBytes - 1024;          // after control block and alignment slack
+  const bool resident = (p.kblocks * kASlabBytes + 2 * kBTileBytes) <= avail;
+  int stages = resident ? (avail - p.kblocks * kASlabBytes) / kBTileBytes : avail / (kASlabBytes + kBTileBytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.stages = stages;
+  const size_t smem = kCtlBytes + 1024 +
+                      (resident ? (size_t)p.kblocks * kASlabBytes + (size_t)stages * kBTileBytes
+                                : (size_t)stages * (kASlabBytes + kBTileBytes));
+  const int sms = num_sms();
+  const int grid = p.n_row_tiles < sms ? p.n_row_tiles : sms;
+  if (mode == 0)
+    return resident ? launch_variant<true, 0>(map_img, map_txt, p, thr, grid, smem, stream)
+                    : launch_variant<false, 0>(map_img, map_txt, p, thr, grid, smem, stream);
+  return resident ? launch_variant<true, 1>(map_img, map_txt, p, thr, grid, smem, stream)
+                  : launch_variant<false, 1>(map_img, map_txt, p, thr, grid, smem, stream);
+}
+
+}  // namespace ccal
+
+using namespace ccal;
+
+extern "C" int ccal_score_fused(const void* img, const void* txt, const float* class_conf, float logit_scale,
+                                int64_t n, int c, int d, int dtype, int32_t* pred_out, float* conf_out,
+                                float* rowmax_out, const int64_t* labels, const double* thresholds_host, int n_thr,
+                                unsigned long long* table, ccal_stream_t stream) {
+  if (n == 0) return CCAL_OK;
+  ScoreParams p{};
+  ThrBlock thr{};
+  p.scale = logit_scale;
+  p.class_conf = class_conf;
+  p.pred_out = pred_out;
+  p.conf_out = conf_out;
+  p.rowmax_out = rowmax_out;
+  p.labels = reinterpret_cast<const long long*>(labels);
+  p.table = table;
+  p.n_thr = 0;
+  if (table != nullptr) {
+    CCAL_REQUIRE(labels != nullptr, "ccal_score_fused: labels are required when a bin table is requested");
+    CCAL_REQUIRE(n_thr >= 0 && n_thr <= CCAL_MAX_THRESHOLDS, "ccal_score_fused: n_thr out of range");
+    CCAL_REQUIRE(n_thr == 0 || thresholds_host != nullptr, "ccal_score_fused: thresholds NULL");
+    CCAL_REQUIRE(n < (1ll << 32), "ccal_score_fused: n must be < 2^32 per call when binning");
+    p.n_thr = n_thr;
+    for (int i = 0; i < n_thr; ++i) thr.t[i] = ceil_to_f32(thresholds_host[i]);
+  }
+  CCAL_REQUIRE(logit_scale > 0.f, "ccal_score_fused: logit_scale must be positive");
+  return run_fused(0, img, txt, n, c, d, dtype, p, thr, (cudaStream_t)stream);
+}
+
+extern "C" int ccal_ts_loss_grad(const void* img, const void* txt, const int64_t* labels, float log_scale,
+                                 int64_t n, int c, int d, int dtype, float* row_ws, double* out2,
+                                 ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE(n >= 1, "ccal_ts_loss_grad: n must be >= 1");
+  CCAL_REQUIRE(labels && row_ws && out2, "ccal_ts_loss_grad: NULL pointer");
+  ScoreParams p{};
+  ThrBlock thr{};
+  p.scale = expf(log_scale);
+  p.labels = reinterpret_cast<const long long*>(labels);
+  p.row_ws = row_ws;
+  int rc = run_fused(1, img, txt, n, c, d, dtype, p, thr, stream);
+  if (rc) return rc;
+  ts_reduce_kernel<<<1, 1024, 0, stream>>>(row_ws, (long long)n, out2);
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}

@@ -1,0 +1,45 @@
+"""The metric half of the reference's evaluators/vl_evaluator.py (`VLClassification.evaluate`,
+reference :59-116): accuracy, error, mean confidence, ECE, MCE, ACE (and PIECE when a proximity
+vector is given), as percentages in the reference's result keys.
+
+In scope: argmax / confidence gather / accuracy / mean confidence (:65-84) and the calibration
+metrics (:86-92).  Out of scope: macro-F1 (sklearn, host-side) and the reliability plot
+(matplotlib) - the per-bin table needed to draw it is returned under "bin_table".
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import native
+from .. import table_math as tm
+from ..tools import metrics
+
+
+def evaluate_pred_conf(preds, confs, labels, ece_bins: int = 10, piece_bins: int = 10, proximity=None,
+                       group=None) -> "OrderedDict[str, float]":
+    """Metrics from per-image (pred, conf, label); numpy or CUDA tensors."""
+    table = metrics.bin_stats(confs, preds, labels, ece_bins, group)
+    results = OrderedDict()
+    acc = 100.0 * tm.accuracy(table)
+    results["accuracy"] = acc
+    results["error_rate"] = 100.0 - acc
+    results["confidence"] = tm.mean_confidence(table)
+    results["ece"] = 100.0 * float(tm.ece_from_table(table))
+    results["mce"] = 100.0 * float(tm.mce_from_table(table))
+    results["ace"] = 100.0 * float(metrics.AdaptiveECE(confs, preds, labels, ece_bins, group=group))
+    if proximity is not None:
+        results["piece"] = 100.0 * float(metrics.PIECE(confs, proximity, preds, labels, piece_bins, ece_bins,
+                                                       group=group))
+    results["bin_table"] = table
+    return results
+
+
+def evaluate(probs, labels, text_proximity=None, ece_bins: int = 10, piece_bins: int = 10):
+    """Reference signature: a full probability matrix in, the result dict out."""
+    p = probs if isinstance(probs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(probs))
+    p = p.to(device="cuda", dtype=torch.float32).contiguous()
+    pred, conf = native.row_argmax(p)              # preds = argmax(probs), confs = probs[i, preds_i]
+    return evaluate_pred_conf(pred, conf, labels, ece_bins, piece_bins, text_proximity)

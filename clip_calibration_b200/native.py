@@ -1,0 +1,322 @@
+"""Tensor-level entry points over the C ABI (include/ccal.h).
+
+PyTorch is plumbing only: it owns device memory and the CUDA stream.  Every function takes CUDA
+tensors, passes raw device pointers to libccal.so and launches on torch's current stream.
+Nothing here computes on the CPU or through ATen kernels, and nothing falls back.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CCAL_BF16, CCAL_F16, FX_SHIFT, MAX_K, MAX_THRESHOLDS
+
+_DTYPES = {torch.bfloat16: CCAL_BF16, torch.float16: CCAL_F16}
+_launches = 0     # kernels launched by this library in this process (bench.py reports it)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _count(n: int) -> None:
+    global _launches
+    _launches += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(name: str, t: torch.Tensor, dtype=None, ndim=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise _lib.CcalError(f"{name}: tensor is on {t.device}; this library only runs on an sm_100 GPU "
+                             "(there is no CPU path)")
+    if dtype is not None and t.dtype not in (dtype if isinstance(dtype, (tuple, list)) else (dtype,)):
+        raise ValueError(f"{name}: dtype {t.dtype} not supported here (want {dtype})")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dimensions, got shape {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def new_table(n_thr: int, n_thr2: int = 0, device=None) -> torch.Tensor:
+    """Zeroed bin table [(n_thr2+1), (n_thr+1), 3] (int64 view of the unsigned counters)."""
+    shape = (n_thr + 1, 3) if n_thr2 == 0 else (n_thr2 + 1, n_thr + 1, 3)
+    return torch.zeros(shape, dtype=torch.int64, device=device or torch.device("cuda"))
+
+
+def table_to_numpy(table: torch.Tensor) -> np.ndarray:
+    return table.detach().cpu().numpy().view(np.uint64)
+
+
+# --------------------------------------------------------------------------------------
+# K2  fused scoring
+# --------------------------------------------------------------------------------------
+def score_fused(img: torch.Tensor, txt: torch.Tensor, class_conf: Optional[torch.Tensor] = None,
+                logit_scale: float = 100.0, labels: Optional[torch.Tensor] = None,
+                thresholds: Optional[Sequence[float]] = None, table: Optional[torch.Tensor] = None,
+                want_pred: bool = True, want_conf: bool = True, want_rowmax: bool = False):
+    """pred / confidence (and optionally the accumulated bin table) of
+    softmax(cc[pred] * logit_scale * img @ txt.T) without materialising logits.
+    Returns (pred int32 [N] | None, conf float32 [N] | None, rowmax float32 [N] | None)."""
+    lib = _lib.load()
+    img = _need_cuda("img", img, (torch.bfloat16, torch.float16), 2)
+    txt = _need_cuda("txt", txt, img.dtype, 2)
+    if img.shape[1] != txt.shape[1]:
+        raise ValueError(f"feature widths differ: img {tuple(img.shape)} vs txt {tuple(txt.shape)}")
+    n, d = img.shape
+    c = txt.shape[0]
+    if class_conf is not None:
+        class_conf = _need_cuda("class_conf", class_conf, torch.float32, 1)
+        if class_conf.numel() != c:
+            raise ValueError(f"class_conf has {class_conf.numel()} entries for {c} classes")
+    dev = img.device
+    pred = torch.empty(n, dtype=torch.int32, device=dev) if want_pred else None
+    conf = torch.empty(n, dtype=torch.float32, device=dev) if want_conf else None
+    rowmax = torch.empty(n, dtype=torch.float32, device=dev) if want_rowmax else None
+    thr_arr, n_thr = _lib.doubles(thresholds if thresholds is not None else [])
+    if table is not None:
+        if labels is None or thresholds is None:
+            raise ValueError("labels and thresholds are required when a bin table is requested")
+        labels = _need_cuda("labels", labels, torch.int64, 1)
+        table = _need_cuda("table", table, torch.int64)
+        if table.numel() != 3 * (n_thr + 1):
+            raise ValueError(f"table has {table.numel()} entries, expected {3 * (n_thr + 1)}")
+        if labels.numel() != n:
+            raise ValueError("labels length differs from the number of images")
+    if n == 0:
+        return pred, conf, rowmax
+    with torch.cuda.device(dev):
+        rc = lib.ccal_score_fused(_ptr(img), _ptr(txt), _ptr(class_conf), float(logit_scale), n, c, d,
+                                  _DTYPES[img.dtype], _ptr(pred), _ptr(conf), _ptr(rowmax),
+                                  _ptr(labels) if table is not None else None, thr_arr, n_thr,
+                                  _ptr(table), _stream())
+    _lib.check(rc, "ccal_score_fused")
+    _count(1)
+    return pred, conf, rowmax
+
+
+# --------------------------------------------------------------------------------------
+# K5  temperature-scaling loss and gradient
+# --------------------------------------------------------------------------------------
+def ts_loss_grad(img: torch.Tensor, txt: torch.Tensor, labels: torch.Tensor, log_scale: float):
+    """(loss, d loss / d log_scale) of cross_entropy(exp(log_scale) * img @ txt.T, labels) as a
+    float64 CUDA tensor of 2 elements (no host sync)."""
+    lib = _lib.load()
+    img = _need_cuda("img", img, (torch.bfloat16, torch.float16), 2)
+    txt = _need_cuda("txt", txt, img.dtype, 2)
+    labels = _need_cuda("labels", labels, torch.int64, 1)
+    n, d = img.shape
+    c = txt.shape[0]
+    if labels.numel() != n:
+        raise ValueError("labels length differs from the number of images")
+    ws = torch.empty(2 * n, dtype=torch.float32, device=img.device)
+    out = torch.empty(2, dtype=torch.float64, device=img.device)
+    with torch.cuda.device(img.device):
+        rc = lib.ccal_ts_loss_grad(_ptr(img), _ptr(txt), _ptr(labels), float(log_scale), n, c, d,
+                                   _DTYPES[img.dtype], _ptr(ws), _ptr(out), _stream())
+    _lib.check(rc, "ccal_ts_loss_grad")
+    _count(2)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# K1  kNN + DAC fit
+# --------------------------------------------------------------------------------------
+def knn_l2(ref: torch.Tensor, query: torch.Tensor, k: int, drop_first: bool = False):
+    lib = _lib.load()
+    ref = _need_cuda("ref", ref, torch.float32, 2)
+    query = _need_cuda("query", query, torch.float32, 2)
+    if ref.shape[1] != query.shape[1]:
+        raise ValueError("feature widths differ")
+    nq, d = query.shape
+    dist = torch.empty((nq, k), dtype=torch.float32, device=ref.device)
+    idx = torch.empty((nq, k), dtype=torch.int32, device=ref.device)
+    with torch.cuda.device(ref.device):
+        rc = lib.ccal_knn_l2(_ptr(ref), _ptr(query), ref.shape[0], nq, d, int(k), int(bool(drop_first)),
+                             _ptr(dist), _ptr(idx), _stream())
+    _lib.check(rc, "ccal_knn_l2")
+    _count(1 if nq else 0)
+    return dist, idx
+
+
+def dac_fit(base_zs, cur_zs, base_tuned, cur_tuned, k: int):
+    """-> (class_conf [C] f32, knn_idx_zs [C,k] i32, knn_idx_tuned, knn_dist_zs [C,k] f32, knn_dist_tuned)"""
+    lib = _lib.load()
+    base_zs = _need_cuda("base_text_features_zs", base_zs, torch.float32, 2)
+    cur_zs = _need_cuda("current_text_features_zs", cur_zs, torch.float32, 2)
+    base_tuned = _need_cuda("base_text_features_tuned", base_tuned, torch.float32, 2)
+    cur_tuned = _need_cuda("current_text_features_tuned", cur_tuned, torch.float32, 2)
+    b, d = base_zs.shape
+    c = cur_zs.shape[0]
+    if base_tuned.shape != base_zs.shape or cur_tuned.shape != cur_zs.shape or cur_zs.shape[1] != d:
+        raise ValueError("zero-shot and tuned feature matrices must have matching shapes")
+    dev = base_zs.device
+    cc = torch.empty(c, dtype=torch.float32, device=dev)
+    iz = torch.empty((c, k), dtype=torch.int32, device=dev)
+    it = torch.empty((c, k), dtype=torch.int32, device=dev)
+    dz = torch.empty((c, k), dtype=torch.float32, device=dev)
+    dt = torch.empty((c, k), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.ccal_dac_fit(_ptr(base_zs), _ptr(cur_zs), _ptr(base_tuned), _ptr(cur_tuned), b, c, d, int(k),
+                              _ptr(cc), _ptr(iz), _ptr(it), _ptr(dz), _ptr(dt), _stream())
+    _lib.check(rc, "ccal_dac_fit")
+    _count(3 if c else 0)
+    return cc, iz, it, dz, dt
+
+
+# --------------------------------------------------------------------------------------
+# K4  materialised logits
+# --------------------------------------------------------------------------------------
+def dac_predict_logits_(logits: torch.Tensor, class_conf: torch.Tensor) -> torch.Tensor:
+    """In place: logits[i,:] *= class_conf[argmax_j logits[i,j]].  Returns pred (int32)."""
+    lib = _lib.load()
+    if not (logits.is_cuda and logits.is_contiguous() and logits.dtype == torch.float32 and logits.dim() == 2):
+        raise ValueError("logits must be a contiguous float32 CUDA matrix (it is modified in place)")
+    class_conf = _need_cuda("class_conf", class_conf, torch.float32, 1)
+    n, c = logits.shape
+    if class_conf.numel() != c:
+        raise ValueError(f"class_conf has {class_conf.numel()} entries for {c} classes")
+    pred = torch.empty(n, dtype=torch.int32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        rc = lib.ccal_dac_predict_logits(_ptr(logits), _ptr(class_conf), n, c, _ptr(pred), _stream())
+    _lib.check(rc, "ccal_dac_predict_logits")
+    _count(1 if n else 0)
+    return pred
+
+
+def logits_confidence(logits: torch.Tensor, class_conf: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    logits = _need_cuda("logits", logits, torch.float32, 2)
+    if class_conf is not None:
+        class_conf = _need_cuda("class_conf", class_conf, torch.float32, 1)
+    n, c = logits.shape
+    pred = torch.empty(n, dtype=torch.int32, device=logits.device)
+    conf = torch.empty(n, dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        rc = lib.ccal_logits_confidence(_ptr(logits), _ptr(class_conf), n, c, _ptr(pred), _ptr(conf), _stream())
+    _lib.check(rc, "ccal_logits_confidence")
+    _count(1 if n else 0)
+    return pred, conf
+
+
+def dac_softmax_logits_(logits: torch.Tensor, class_conf: Optional[torch.Tensor] = None):
+    """In place: logits[i,:] <- softmax(class_conf[pred_i] * logits[i,:]).  Returns (pred, conf)."""
+    lib = _lib.load()
+    if not (logits.is_cuda and logits.is_contiguous() and logits.dtype == torch.float32 and logits.dim() == 2):
+        raise ValueError("logits must be a contiguous float32 CUDA matrix (it is modified in place)")
+    if class_conf is not None:
+        class_conf = _need_cuda("class_conf", class_conf, torch.float32, 1)
+    n, c = logits.shape
+    pred = torch.empty(n, dtype=torch.int32, device=logits.device)
+    conf = torch.empty(n, dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        rc = lib.ccal_dac_softmax_logits(_ptr(logits), _ptr(class_conf), n, c, _ptr(pred), _ptr(conf), _stream())
+    _lib.check(rc, "ccal_dac_softmax_logits")
+    _count(1 if n else 0)
+    return pred, conf
+
+
+def row_argmax(values: torch.Tensor):
+    """(first argmax int32 [N], row max float32 [N]) of an [N, C] float32 matrix."""
+    lib = _lib.load()
+    values = _need_cuda("values", values, torch.float32, 2)
+    n, c = values.shape
+    pred = torch.empty(n, dtype=torch.int32, device=values.device)
+    mx = torch.empty(n, dtype=torch.float32, device=values.device)
+    with torch.cuda.device(values.device):
+        rc = lib.ccal_row_argmax(_ptr(values), n, c, _ptr(pred), _ptr(mx), _stream())
+    _lib.check(rc, "ccal_row_argmax")
+    _count(1 if n else 0)
+    return pred, mx
+
+
+# --------------------------------------------------------------------------------------
+# K3  bin statistics and exact order statistics
+# --------------------------------------------------------------------------------------
+def bin_stats(conf: torch.Tensor, pred: torch.Tensor, gt: torch.Tensor, thresholds: Sequence[float],
+              key2: Optional[torch.Tensor] = None, thresholds2: Optional[Sequence[float]] = None,
+              table: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Accumulate {count, n_correct, sum conf*2^40} per bin; bin = #(thresholds <= conf)."""
+    lib = _lib.load()
+    conf = _need_cuda("conf", conf, (torch.float32, torch.float64), 1)
+    pred = _need_cuda("pred", pred, (torch.int32, torch.int64), 1)
+    gt = _need_cuda("gt", gt, torch.int64, 1)
+    n = conf.numel()
+    if pred.numel() != n or gt.numel() != n:
+        raise ValueError("conf, pred and gt must have the same length")
+    thr, n_thr = _lib.doubles(thresholds)
+    thr2, n_thr2 = _lib.doubles(thresholds2 if thresholds2 is not None else [])
+    if (key2 is None) != (n_thr2 == 0):
+        raise ValueError("key2 and thresholds2 must be given together")
+    if key2 is not None:
+        key2 = _need_cuda("key2", key2, torch.float32, 1)
+        if key2.numel() != n:
+            raise ValueError("key2 length differs")
+    if table is None:
+        table = new_table(n_thr, n_thr2, conf.device)
+    elif table.numel() != 3 * (n_thr + 1) * (n_thr2 + 1) or table.dtype != torch.int64 or not table.is_cuda:
+        raise ValueError("table has the wrong size / dtype / device")
+    with torch.cuda.device(conf.device):
+        rc = lib.ccal_bin_stats(_ptr(conf), int(conf.dtype == torch.float64), _ptr(pred),
+                                int(pred.dtype == torch.int64), _ptr(gt), n, thr, n_thr,
+                                _ptr(key2), thr2, n_thr2, _ptr(table), _stream())
+    _lib.check(rc, "ccal_bin_stats")
+    _count(1 if n else 0)
+    return table
+
+
+def radix_hist(keys: torch.Tensor, level: int, prefixes: Optional[Sequence[int]] = None,
+               hist: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = _lib.load()
+    keys = _need_cuda("keys", keys, torch.float32, 1)
+    pf, n_pf = _lib.uint32s(prefixes if prefixes is not None else [])
+    rows = 1 if level == 0 else n_pf
+    if hist is None:
+        hist = torch.zeros((rows, 65536), dtype=torch.int32, device=keys.device)
+    with torch.cuda.device(keys.device):
+        rc = lib.ccal_radix_hist(_ptr(keys), keys.numel(), int(level), pf, n_pf, _ptr(hist), _stream())
+    _lib.check(rc, "ccal_radix_hist")
+    _count(1 if keys.numel() else 0)
+    return hist
+
+
+def order_statistics(keys: torch.Tensor, ranks: Sequence[int], group=None) -> np.ndarray:
+    """Exact values of the given 0-based ranks of the (globally sorted, non-negative) float32
+    keys.  Two 16-bit radix-histogram passes on the device; with `group` the histograms are
+    summed over ranks (torch.distributed all-reduce) so every rank gets the global answer."""
+    keys = _need_cuda("keys", keys, torch.float32, 1)
+    h0 = radix_hist(keys, 0)
+    if group is not None:
+        torch.distributed.all_reduce(h0, group=group)
+    c0 = np.cumsum(h0.cpu().numpy().astype(np.int64).ravel())
+    total = int(c0[-1])
+    ranks = [int(r) for r in ranks]
+    if any(r < 0 or r >= total for r in ranks):
+        raise ValueError("rank out of range")
+    hi = np.searchsorted(c0, np.asarray(ranks), side="right")          # bucket holding each rank
+    uniq = sorted(set(int(h) for h in hi))
+    out = np.empty(len(ranks), np.float32)
+    for lo in range(0, len(uniq), 64):
+        part = uniq[lo:lo + 64]
+        h1 = radix_hist(keys, 1, part)
+        if group is not None:
+            torch.distributed.all_reduce(h1, group=group)
+        c1 = np.cumsum(h1.cpu().numpy().astype(np.int64), axis=1)
+        for j, r in enumerate(ranks):
+            if int(hi[j]) in part:
+                row = part.index(int(hi[j]))
+                before = int(c0[hi[j] - 1]) if hi[j] > 0 else 0
+                low = int(np.searchsorted(c1[row], r - before, side="right"))
+                out[j] = np.array([(int(hi[j]) << 16) | low], np.uint32).view(np.float32)[0]
+    return out

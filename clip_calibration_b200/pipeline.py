@@ -1,0 +1,151 @@
+"""One-call scoring + calibration + ECE over image shards (additive API).
+
+What the reference does across VLBaseLearner.test (trainers/classification/base_learner.py:84-144),
+VLCalibration.fit/predict (trainers/calibration/vl_calibrator.py:71-109) and
+VLClassification.evaluate (evaluators/vl_evaluator.py:59-92) - contraction, DAC, softmax, argmax,
+confidence gather, ECE/MCE/accuracy - is here one fused kernel per image shard plus, across the
+GPUs of a box, ONE all-reduce of a 33-integer bin table.
+
+Sharding: images (rows) are independent, so each rank owns a contiguous slice of the images;
+the text features, the per-class multipliers and the bin edges are replicated (the DAC fit is
+recomputed on every rank: it is tiny and avoids a broadcast).  The table is integer / fixed
+point, so the 1-GPU and the N-GPU results are bit-identical.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import native
+from . import table_math as tm
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous, balanced [lo, hi) slice of n images for `rank` of `world`."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class CalibratedScorer:
+    """Text side of the problem, resident on this rank's GPU, plus the running bin table."""
+
+    def __init__(self, text_features, class_conf=None, logit_scale: float = 100.0, n_bins: int = 10,
+                 operand_dtype=torch.bfloat16, group=None, device=None):
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.operand_dtype = operand_dtype
+        self.txt = self._features(text_features)
+        self.class_conf = None
+        if class_conf is not None:
+            cc = class_conf if isinstance(class_conf, torch.Tensor) else torch.from_numpy(np.asarray(class_conf))
+            self.class_conf = cc.to(device=self.device, dtype=torch.float32).contiguous()
+        self.logit_scale = float(logit_scale)
+        self.n_bins = int(n_bins)
+        self.thresholds = tm.uniform_thresholds(self.n_bins)
+        self.group = group
+        self.table = native.new_table(self.n_bins, device=self.device)
+        self._copy_stream = None
+
+    # ------------------------------------------------------------------ construction helpers
+    def _features(self, x) -> torch.Tensor:
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        return t.detach().to(self.device).to(self.operand_dtype).contiguous()
+
+    @classmethod
+    def from_dac(cls, base_zs, cur_zs, base_tuned, cur_tuned, k: int = 5, **kw):
+        """Fit DAC on the four text matrices (this rank, redundantly) and score against the tuned
+        test-vocabulary features - what VLBaseLearner.test + build_dac_calibrator set up
+        (base_learner.py:117-119, vl_calibrator.py:155-180)."""
+        from .trainers.calibration.distanse_aware_calibration import DistanseAwareCalibration
+        dac = DistanseAwareCalibration()
+        dac.fit(base_zs, cur_zs, base_tuned, cur_tuned, k)
+        obj = cls(cur_tuned, dac.class_confidence_device, **kw)
+        obj.dac = dac
+        return obj
+
+    # ------------------------------------------------------------------ scoring
+    def reset(self):
+        self.table.zero_()
+
+    def score(self, image_features, labels=None, accumulate: bool = True):
+        """Device-resident shard -> (pred, conf); with labels the shard is also binned into the
+        running table.  No logits are materialised."""
+        img = self._features(image_features)
+        if labels is not None:
+            labels = (labels if isinstance(labels, torch.Tensor) else torch.from_numpy(np.asarray(labels)))
+            labels = labels.to(device=self.device, dtype=torch.int64)
+        use_table = labels is not None and accumulate
+        pred, conf, _ = native.score_fused(img, self.txt, self.class_conf, self.logit_scale, labels,
+                                           self.thresholds if use_table else None, self.table if use_table else None)
+        return pred, conf
+
+    def accumulate_host(self, image_features: torch.Tensor, labels: torch.Tensor, chunk_rows: int = 131072,
+                        keep_outputs: bool = False):
+        """End-to-end path for HOST inputs (ideally pinned): the shard is cut into row chunks,
+        chunk i+1 is copied host->device on a side stream while chunk i is being scored, and
+        only the bin table (and optionally pred/conf) ever comes back."""
+        if image_features.is_cuda:
+            raise ValueError("accumulate_host expects host tensors; use score() for device tensors")
+        if image_features.dtype != self.operand_dtype:
+            raise ValueError(f"host features must already be {self.operand_dtype} (convert once, outside the hot loop)")
+        n, d = image_features.shape
+        labels = labels.to(torch.int64)
+        comp = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        copy = self._copy_stream
+        chunk_rows = max(128, min(int(chunk_rows), n))
+        bufs = [torch.empty((chunk_rows, d), dtype=self.operand_dtype, device=self.device) for _ in range(2)]
+        lbufs = [torch.empty(chunk_rows, dtype=torch.int64, device=self.device) for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        preds, confs = [], []
+        copy.wait_stream(comp)
+        for i, lo in enumerate(range(0, n, chunk_rows)):
+            hi = min(n, lo + chunk_rows)
+            b = i & 1
+            with torch.cuda.stream(copy):
+                if i >= 2:
+                    copy.wait_event(consumed[b])
+                bufs[b][: hi - lo].copy_(image_features[lo:hi], non_blocking=True)
+                lbufs[b][: hi - lo].copy_(labels[lo:hi], non_blocking=True)
+                copied[b].record(copy)
+            comp.wait_event(copied[b])
+            pred, conf, _ = native.score_fused(bufs[b][: hi - lo], self.txt, self.class_conf, self.logit_scale,
+                                               lbufs[b][: hi - lo], self.thresholds, self.table,
+                                               want_pred=keep_outputs, want_conf=keep_outputs)
+            consumed[b].record(comp)
+            if keep_outputs:
+                preds.append(pred)
+                confs.append(conf)
+        if keep_outputs:
+            return torch.cat(preds), torch.cat(confs)
+        return None
+
+    # ------------------------------------------------------------------ results
+    def reduced_table(self) -> np.ndarray:
+        """The bin table summed over all ranks of `group` (one NCCL all-reduce of
+        3*(n_bins+1) int64 on the compute stream), as a host uint64 array."""
+        t = self.table
+        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                      and torch.distributed.get_world_size() > 1):
+            t = t.clone()
+            torch.distributed.all_reduce(t, group=self.group)
+        return native.table_to_numpy(t)
+
+    def summary(self) -> dict:
+        table = self.reduced_table()
+        return {"n": tm.total_count(table), "accuracy": tm.accuracy(table), "confidence": tm.mean_confidence(table),
+                "ece": float(tm.ece_from_table(table)), "mce": float(tm.mce_from_table(table)), "table": table}
+
+
+def score_and_ece(image_features, text_features, labels, class_conf=None, logit_scale: float = 100.0,
+                  n_bins: int = 10, operand_dtype=torch.bfloat16, group=None) -> dict:
+    """features -> {accuracy, confidence, ece, mce, table, pred, conf} in one fused pass."""
+    scorer = CalibratedScorer(text_features, class_conf, logit_scale, n_bins, operand_dtype, group)
+    pred, conf = scorer.score(image_features, labels)
+    out = scorer.summary()
+    out["pred"], out["conf"] = pred, conf
+    return out

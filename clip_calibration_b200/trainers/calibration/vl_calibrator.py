@@ -1,0 +1,82 @@
+"""Drop-in for the DAC + softmax branch of the reference's trainers/calibration/vl_calibrator.py
+(`VLCalibration.__init__ / fit / predict / build_dac_calibrator`, reference :30-109, :155-180).
+
+In scope: DAC (dac_flag) followed by softmax.  The bin-based / density-ratio base calibrators
+(reference :112-150; netcal / statsmodels CPU statistics) are out of scope: requesting one
+raises NotImplementedError instead of silently skipping it.
+
+`predict(logits, proximity)` keeps the reference contract and returns probabilities [N, C].
+`predict_confidence` / `predict_from_features` are the additive routes that return only
+(pred, conf) - all the evaluator reads (evaluators/vl_evaluator.py:68, :83).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ... import native
+from .distanse_aware_calibration import DistanseAwareCalibration
+
+
+class VLCalibration():
+
+    def __init__(self, cfg, base_calibration_mode=None, base_bin_calibrator_name=None, dac_flag=False,
+                 procal_flag=False, val_dict=None, text_feature_dict=None):
+        if base_calibration_mode is not None:
+            raise NotImplementedError(
+                "base calibrators (scaling_based / bin_based; netcal + statsmodels in the reference) are outside "
+                "the accelerated path; use the reference's VLCalibration for them")
+        self.cfg = cfg
+        self.base_calibration_mode = None
+        self.base_bin_calibrator_name = base_bin_calibrator_name
+        self.dac_flag = dac_flag
+        self.procal_flag = procal_flag
+        self.text_feature_dict = text_feature_dict
+        self.k_dac = cfg.CALIBRATION.DAC.K if cfg is not None else 5
+        self.val_dict = val_dict
+        if val_dict is not None and "val_image_knn_dists" in val_dict:
+            # distances to proximity (reference :68)
+            self.val_image_proximity = np.exp(-np.mean(val_dict["val_image_knn_dists"], axis=-1))
+        self.dac_calibrator = None
+        self.base_calibrator = None
+
+    def fit(self):
+        self.dac_calibrator = None
+        self.base_calibrator = None
+        if self.dac_flag:
+            self.dac_calibrator = self.build_dac_calibrator(self.text_feature_dict, self.k_dac)
+
+    def build_dac_calibrator(self, text_feature_dict, k_dac):
+        dac_calibrator = DistanseAwareCalibration()
+        dac_calibrator.fit(text_feature_dict["base_text_features_zs"], text_feature_dict["current_text_features_zs"],
+                           text_feature_dict["base_text_features_tuned"],
+                           text_feature_dict["current_text_features_tuned"], k=k_dac)
+        return dac_calibrator
+
+    # ------------------------------------------------------------------ reference contract
+    def predict(self, logits, test_proximity):
+        assert logits.shape[0] == test_proximity.shape[0], \
+            f"Shape mismatch: logits shape {logits.shape[0]} != test_proximity shape {test_proximity.shape[0]}"
+        as_numpy = not isinstance(logits, torch.Tensor)
+        x = torch.from_numpy(np.ascontiguousarray(logits)) if as_numpy else logits.detach()
+        # DAC scaling + softmax happen in place in one CUDA kernel (ccal_dac_softmax_logits); the
+        # [N, C] probability matrix exists only because the reference contract returns it.
+        # Without DAC the reference keeps float64 probabilities; here they are float32.
+        work = x.to(device="cuda", dtype=torch.float32, copy=True).contiguous()
+        cc = self.dac_calibrator._cc() if self.dac_calibrator is not None else None
+        native.dac_softmax_logits_(work, cc)
+        return work.cpu().numpy() if as_numpy else work
+
+    # ------------------------------------------------------------------ additive
+    def predict_confidence(self, logits):
+        cc = self.dac_calibrator._cc() if self.dac_calibrator is not None else None
+        as_numpy = not isinstance(logits, torch.Tensor)
+        x = torch.from_numpy(np.ascontiguousarray(logits)) if as_numpy else logits.detach()
+        pred, conf = native.logits_confidence(x.to(device="cuda", dtype=torch.float32).contiguous(), cc)
+        return (pred.cpu().numpy().astype(np.int64), conf.cpu().numpy()) if as_numpy else (pred, conf)
+
+    def predict_from_features(self, image_features, text_features=None, logit_scale=100.0):
+        dac = self.dac_calibrator if self.dac_calibrator is not None else DistanseAwareCalibration()
+        if text_features is None:
+            text_features = self.text_feature_dict["current_text_features_tuned"]
+        return dac.predict_from_features(image_features, text_features, logit_scale)

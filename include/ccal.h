@@ -1,0 +1,161 @@
+/*
+ * ccal.h — C ABI of the B200-native scoring + calibration + calibration-metrics path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.  The
+ * reference (ml-stat-Sustech/CLIP_Calibration) is pure Python, so the binding a maintainer
+ * adds is a ctypes stub (shown in INTEGRATION.md); each entry point names the reference
+ * code it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless its name ends in _host;
+ *   - row-major, contiguous; feature matrices are [rows, D] with D contiguous;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it, the caller
+ *     synchronises;
+ *   - return value 0 = OK, otherwise a CCAL_ERR_* code; ccal_last_error() gives the
+ *     thread-local message.  There is no CPU fallback: a device that is not sm_100 fails.
+ *   - bin tables are [(n_thr+1)][3] unsigned 64-bit {count, n_correct, sum(round(conf*2^40))},
+ *     bin index of a confidence x = number of thresholds <= x (compared in double).
+ *     Kernels ACCUMULATE into the table (the caller zeroes it), so shards / chunks / ranks
+ *     add up exactly and in any order.
+ */
+#ifndef CCAL_H_
+#define CCAL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCAL_VERSION 100
+
+enum {
+  CCAL_OK = 0,
+  CCAL_ERR_BAD_ARG = 1,      /* null pointer, negative size, unsupported shape / alignment */
+  CCAL_ERR_UNSUPPORTED = 2,  /* device is not sm_100 / feature width not supported          */
+  CCAL_ERR_CUDA = 3          /* a CUDA runtime / driver call failed                         */
+};
+
+/* operand dtypes of the feature matrices */
+enum { CCAL_F32 = 0, CCAL_F16 = 1, CCAL_BF16 = 2 };
+
+#define CCAL_FX_SHIFT 40        /* fixed-point scale of the per-bin confidence sums        */
+#define CCAL_MAX_THRESHOLDS 63  /* n_thr upper bound (64 bins)                              */
+#define CCAL_MAX_K 16           /* nearest-neighbour count upper bound                      */
+
+typedef void* ccal_stream_t;
+
+#if defined(__GNUC__)
+#define CCAL_API __attribute__((visibility("default")))
+#else
+#define CCAL_API
+#endif
+
+CCAL_API int ccal_version(void);
+CCAL_API const char* ccal_last_error(void);
+
+/* 0 if the current device can run this library (compute capability 10.x). */
+CCAL_API int ccal_check_device(void);
+
+/* ---- K2: fused scoring --------------------------------------------------------------
+ * Replaces, without ever materialising logits:
+ *   logits = logit_scale * image_features @ text_features.t()
+ *                                   (trainers/classification/zsclip.py:97-102, coop.py:215-217,
+ *                                    trainers/calibration/tempscaling.py:53-56)
+ *   DistanseAwareCalibration.predict (trainers/calibration/distanse_aware_calibration.py:49-58)
+ *   scipy softmax                    (trainers/calibration/vl_calibrator.py:91)
+ *   argmax + confidence gather       (evaluators/vl_evaluator.py:68, :83)
+ *   and, when `table` is given, the binning of tools/metrics.py:104-127.
+ *
+ * img [n,d], txt [c,d] in `dtype` (CCAL_BF16 or CCAL_F16), d a multiple of 64 and <= 1024,
+ * base pointers 16-byte aligned.  class_conf [c] float or NULL (= all ones, plain softmax).
+ * pred_out [n] int32, conf_out [n] float, rowmax_out [n] float (logit_scale * max cosine) may
+ * each be NULL.  labels [n] int64 + thresholds_host [n_thr] (HOST doubles) + table (device)
+ * enable the fused binning; pass table = NULL to skip it.
+ * Pass 1 = row max / argmax over all text tiles; pass 2 recomputes the tiles and sums
+ * exp(cc[pred] * (logit - max)); confidence = 1 / sum.  Ties: lowest class index.
+ */
+CCAL_API int ccal_score_fused(const void* img, const void* txt, const float* class_conf, float logit_scale,
+                     int64_t n, int c, int d, int dtype,
+                     int32_t* pred_out, float* conf_out, float* rowmax_out,
+                     const int64_t* labels, const double* thresholds_host, int n_thr,
+                     unsigned long long* table, ccal_stream_t stream);
+
+/* ---- K5: temperature-scaling objective ------------------------------------------------
+ * loss = F.cross_entropy(exp(log_scale) * img @ txt.T, labels) and d loss / d log_scale, for
+ * trainers/calibration/tempscaling.py:31-41 (ScaleLearner), :53-56, :155-160.
+ * Same operand rules as ccal_score_fused.  row_ws [2*n] float scratch (per-row loss and
+ * gradient terms, reduced in a fixed order => deterministic).  out2 [2] double = {loss, grad}.
+ */
+CCAL_API int ccal_ts_loss_grad(const void* img, const void* txt, const int64_t* labels, float log_scale,
+                      int64_t n, int c, int d, int dtype, float* row_ws, double* out2,
+                      ccal_stream_t stream);
+
+/* ---- K1: k nearest rows by Euclidean distance + the DAC map ---------------------------
+ * ccal_knn_l2: for every query row q_i [nq,d] the kk = min(k, nr) smallest ||r_j - q_i||_2 over
+ * ref rows [nr,d] (fp32), ascending, ties by lowest j.  dist_out [nq,k] (unused tail = +inf),
+ * idx_out [nq,k] (unused tail = -1) may be NULL.  drop_first != 0 computes k+1 and drops the
+ * nearest (trainers/calibration/proximity.py:49-70); otherwise proximity.py:19-46 and the
+ * distance/sort lines of distanse_aware_calibration.py:28-30, :34-36.
+ */
+CCAL_API int ccal_knn_l2(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k,
+                int drop_first, float* dist_out, int32_t* idx_out, ccal_stream_t stream);
+
+/* ccal_dac_fit = DistanseAwareCalibration.fit (distanse_aware_calibration.py:13-46):
+ * class_conf_out[i] = 1 if nearest tuned distance < 0.05 else
+ *                     exp(-sum(top-k tuned)/k) / exp(-sum(top-k zero-shot)/k).
+ * Inputs fp32 [b,d] / [c,d].  The two [c,k] distance buffers are required (they double as
+ * workspace); the two [c,k] index buffers may be NULL.
+ */
+CCAL_API int ccal_dac_fit(const float* base_zs, const float* cur_zs, const float* base_tuned,
+                 const float* cur_tuned, int b, int c, int d, int k,
+                 float* class_conf_out, int32_t* knn_idx_zs_out, int32_t* knn_idx_tuned_out,
+                 float* knn_dist_zs_out, float* knn_dist_tuned_out, ccal_stream_t stream);
+
+/* ---- K4: materialised-logits drop-ins -------------------------------------------------
+ * ccal_dac_predict_logits = DistanseAwareCalibration.predict (:49-58): in place,
+ * logits[i,:] *= class_conf[argmax_j logits[i,j]].  pred_out may be NULL.
+ * ccal_logits_confidence: pred/conf of softmax(class_conf[pred] * logits) without writing the
+ * scaled logits or the probabilities (vl_calibrator.py:91 + vl_evaluator.py:68,:83);
+ * class_conf may be NULL.
+ */
+CCAL_API int ccal_dac_predict_logits(float* logits, const float* class_conf, int64_t n, int c,
+                            int32_t* pred_out, ccal_stream_t stream);
+CCAL_API int ccal_logits_confidence(const float* logits, const float* class_conf, int64_t n, int c,
+                           int32_t* pred_out, float* conf_out, ccal_stream_t stream);
+/* ccal_dac_softmax_logits: VLCalibration.predict (vl_calibrator.py:83-109, DAC + softmax branch):
+ * in place, logits[i,:] <- softmax(class_conf[pred_i] * logits[i,:]); class_conf may be NULL.
+ * ccal_row_argmax: first argmax and row maximum of an [n,c] matrix (evaluators/vl_evaluator.py:68,
+ * :83 on a probability matrix).  Output pointers may be NULL. */
+CCAL_API int ccal_dac_softmax_logits(float* logits, const float* class_conf, int64_t n, int c,
+                            int32_t* pred_out, float* conf_out, ccal_stream_t stream);
+CCAL_API int ccal_row_argmax(const float* values, int64_t n, int c, int32_t* pred_out, float* max_out,
+                    ccal_stream_t stream);
+
+/* ---- K3: bin statistics for ECE / MCE / ACE / PIECE -----------------------------------
+ * tools/metrics.py:104-127 (ECE), :195-206 (MCE), :228-234 (AdaptiveECE) all reduce to
+ * per-bin {count, n_correct, sum conf}.  conf is float (conf_f64 = 0) or double (1).
+ * pred may be int32 (pred_i64 = 0) or int64 (1); gt is int64.
+ * Optional second key (PIECE, :152-168): key2 [n] float with thresholds2_host [n_thr2]; the
+ * table is then [(n_thr2+1)][(n_thr+1)][3].  Pass key2 = NULL, n_thr2 = 0 for the 1-D table.
+ */
+CCAL_API int ccal_bin_stats(const void* conf, int conf_f64, const void* pred, int pred_i64,
+                   const int64_t* gt, int64_t n, const double* thresholds_host, int n_thr,
+                   const float* key2, const double* thresholds2_host, int n_thr2,
+                   unsigned long long* table, ccal_stream_t stream);
+
+/* ---- exact order statistics of float keys (quantile bin edges for ACE / PIECE) ---------
+ * 16-bit radix histograms over the order-preserving bit pattern of non-negative floats.
+ * level 0: hist[65536] += count of (bits >> 16).  level 1: for each of the n_prefix given
+ * high halves, hist[p][65536] += count of (bits & 0xffff) among keys with that high half.
+ * Counts are uint32 (n < 2^32 per call); tables accumulate (caller zeroes) so ranks can be
+ * all-reduced.
+ */
+CCAL_API int ccal_radix_hist(const float* keys, int64_t n, int level, const uint32_t* prefixes_host,
+                    int n_prefix, uint32_t* hist, ccal_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCAL_H_ */

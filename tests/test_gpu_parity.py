@@ -1,0 +1,243 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the oracle and the
+golden vectors produced by the real reference functions.
+
+Tolerances (BASELINE.json north_star): predicted labels and kNN indices bit-exact except ties
+(a "tie row" = reference top-2 logit gap <= 4e-5 * s/100: fp32 accumulation order alone can
+flip those); confidences within 1e-4 relative; ECE within 1e-5 absolute; bin counts exact
+except samples within 1e-6 of a bin edge.
+"""
+import numpy as np
+import pytest
+import torch
+
+from clip_calibration_b200 import native, pipeline, synth
+from clip_calibration_b200 import table_math as tm
+from clip_calibration_b200.tools import metrics
+from clip_calibration_b200.trainers.calibration.distanse_aware_calibration import DistanseAwareCalibration
+from clip_calibration_b200.trainers.calibration import tempscaling, proximity, vl_calibrator
+from oracle import cpu_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TIE_GAP = 4e-5
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def near_edge(conf, n_bins, tol=1e-6):
+    edges = np.linspace(0, 1, n_bins + 1)
+    return np.min(np.abs(conf[:, None].astype(np.float64) - edges[None, :]), axis=1) <= tol
+
+
+# ----------------------------------------------------------------------------- K3
+def test_bin_stats_edge_cases_exact(cuda_lib, golden):
+    g = golden("metric_edge_cases")
+    for name in g["names"]:
+        conf, pred, gt = g[f"{name}_conf"], g[f"{name}_pred"], g[f"{name}_gt"]
+        for nb in (10, 15):
+            tab = metrics.bin_stats(conf, pred, gt, nb)
+            assert np.array_equal(tab, orc.bin_table(conf, pred, gt, tm.uniform_thresholds(nb))), (name, nb)
+            assert abs(metrics.ECE(conf, pred, gt, nb) - float(g[f"{name}_ece{nb}"])) < 1e-7, name
+            assert abs(metrics.MCE(conf, pred, gt, nb) - float(g[f"{name}_mce{nb}"])) < 1e-7, name
+            assert abs(metrics.AdaptiveECE(conf, pred, gt, nb) - float(g[f"{name}_ace{nb}"])) < 1e-7, (name, nb)
+    assert metrics.ECE(np.array([1.0, 0.5], np.float32), np.array([0, 0]), np.array([0, 0]), 10) == 0.25
+    assert isinstance(metrics.ECE(g["single_conf"], g["single_pred"], g["single_gt"]), np.float64)
+
+
+def test_bin_stats_large_random_and_order_statistics(cuda_lib):
+    rng = np.random.default_rng(11)
+    n = 1_000_003
+    conf = np.where(rng.random(n) < 0.05, 1.0, rng.random(n) ** 2).astype(np.float32)
+    pred = rng.integers(0, 7, n).astype(np.int32)
+    gt = rng.integers(0, 7, n)
+    tab = metrics.bin_stats(conf, pred, gt, 15)
+    assert np.array_equal(tab, orc.bin_table(conf, pred, gt, tm.uniform_thresholds(15)))
+    ranks = [0, 1, 17, n // 3, n // 2, n - 2, n - 1]
+    got = native.order_statistics(dev(conf), ranks)
+    assert np.array_equal(got, np.sort(conf)[ranks])
+    small = conf[:150000]
+    assert abs(metrics.AdaptiveECE(small, pred[:150000], gt[:150000], 10)
+               - orc.adaptive_ece(small, pred[:150000], gt[:150000], 10)) < 1e-7
+
+
+def test_piece_matches_reference(cuda_lib, golden):
+    g = golden("proximity_piece")
+    prox = np.exp(-np.mean(g["knn"], axis=-1))
+    for nb in (10, 5):
+        assert abs(metrics.PIECE(g["conf"], prox, g["pred"], g["labels"], nb, 10) - float(g[f"piece{nb}"])) < 1e-7
+
+
+# ----------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("name,ks", [("eurosat", (5,)), ("sun397_l14", (1, 5, 10)), ("imagenet", (5,)), ("openvocab", (5,))])
+def test_dac_fit_matches_reference(cuda_lib, name, ks, golden, synth_case):
+    g, case = golden(name), synth_case(name)
+    for k in ks:
+        dac = DistanseAwareCalibration()
+        dac.fit(case.base_zs, case.txt_zs, case.base_tuned, case.txt_tuned, k)
+        cc_ref = g[f"cc_k{k}"]
+        assert dac.class_confidence.dtype == np.float64 and dac.class_confidence.shape == cc_ref.shape
+        np.testing.assert_allclose(dac.class_confidence, cc_ref, rtol=2e-6)
+        assert np.array_equal(dac.class_confidence == 1.0, cc_ref == 1.0)        # base-class test agrees
+        sel = g[f"fit_sel_k{k}"]
+        kk = min(k, case.n_base)
+        dref = g[f"knn_dist_tuned_k{k}"]
+        dgot = dac.knn_distances_tuned.cpu().numpy()[sel][:, :kk]
+        np.testing.assert_allclose(dgot, dref, rtol=2e-6, atol=1e-7)
+        # indices: exact, except where two candidate distances coincide to fp32 rounding
+        igot = dac.knn_indices_tuned.cpu().numpy()[sel][:, :kk]
+        iref = g[f"knn_idx_tuned_k{k}"]
+        diff = igot != iref
+        if diff.any():
+            assert np.all(np.abs(dgot[diff] - dref[diff]) <= 2e-6 * np.abs(dref[diff]) + 1e-7)
+            assert diff.mean() < 1e-3
+        zgot = dac.knn_indices_zs.cpu().numpy()[sel][:, :kk]
+        assert (zgot != g[f"knn_idx_zs_k{k}"]).mean() < 1e-3
+
+
+def test_dac_fit_k_larger_than_base_and_duplicates(cuda_lib):
+    case = synth.make_case("tiny", 16, 6, 3, 64, 5, 0.3, seed=9)
+    base_zs = case.base_zs.copy(); base_zs[2] = base_zs[1]            # duplicate base row (equal distances)
+    dac = DistanseAwareCalibration()
+    dac.fit(base_zs, case.txt_zs, case.base_tuned, case.txt_tuned, 5)   # k=5 > B=3
+    cc, iz, it, dz, dt = orc.dac_fit(base_zs, case.txt_zs, case.base_tuned, case.txt_tuned, 5)
+    np.testing.assert_allclose(dac.class_confidence, cc, rtol=2e-6)
+    assert np.array_equal(dac.knn_indices_tuned.cpu().numpy()[:, :3], it)
+    assert np.all(dac.knn_indices_tuned.cpu().numpy()[:, 3:] == -1)
+    assert np.array_equal(dac.knn_indices_zs.cpu().numpy()[:, :3], iz)        # ties -> lowest index first
+
+
+def test_proximity_knn(cuda_lib, golden):
+    g = golden("proximity_piece")
+    case = synth.make_case("prox", 600, 40, 20, 512, 5, 0.3, seed=3)
+    val = synth.make_case("proxval", 300, 40, 20, 512, 5, 0.3, seed=4).img
+    np.testing.assert_allclose(proximity.get_knn_dists(val, case.img, 5), g["knn"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(proximity.get_val_image_knn_dists(val, 5), g["knn_self"], rtol=2e-6, atol=2e-7)
+
+
+# ----------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("n,c", [(1, 1), (77, 10), (300, 397), (129, 2048), (65, 2049), (33, 49408)])
+def test_materialised_logits_dropins(cuda_lib, n, c):
+    rng = np.random.default_rng(n * 1000 + c)
+    logits = (rng.standard_normal((n, c)) * 8).astype(np.float32)
+    if c > 3:
+        logits[0, 3] = logits[0, 1] = logits[0].max() + 1.0               # a tie: first index wins
+    cc = (0.9 + 0.1 * rng.random(c)).astype(np.float32)
+    dac = DistanseAwareCalibration()
+    dac.class_confidence = cc.astype(np.float64)
+    before = logits.copy()
+    out = dac.predict(logits.astype(np.float64))
+    assert out.dtype == np.float32 and np.array_equal(logits, before)
+    assert np.array_equal(out, orc.dac_predict(logits, cc))                # fp32 multiply: bit exact
+    probs_ref = orc.softmax_lastaxis(orc.dac_predict(logits, cc))
+    pref, cref = orc.pred_and_conf(probs_ref)
+    pred, conf = dac.predict_confidence(logits)
+    assert np.array_equal(pred, pref)
+    np.testing.assert_allclose(conf, cref, rtol=1e-5)
+    cal = vl_calibrator.VLCalibration(None, dac_flag=True)
+    cal.dac_calibrator = dac
+    probs = cal.predict(logits, np.zeros(n))
+    np.testing.assert_allclose(probs, probs_ref, rtol=2e-5, atol=1e-30)
+
+
+# ----------------------------------------------------------------------------- K2
+def check_scoring(case, cc, pred_ref, conf_ref, gap_ref, ece_ref, counts_ref, dtype=torch.bfloat16):
+    img, txt = dev(case.img, dtype), dev(case.txt_tuned, dtype)
+    labels = dev(case.labels)
+    ccd = dev(cc.astype(np.float32)) if cc is not None else None
+    thr = tm.uniform_thresholds(10)
+    table = native.new_table(10)
+    pred, conf, rowmax = native.score_fused(img, txt, ccd, case.logit_scale, labels, thr, table, want_rowmax=True)
+    torch.cuda.synchronize()
+    pred, conf = pred.cpu().numpy(), conf.cpu().numpy()
+    ties = gap_ref <= TIE_GAP * case.logit_scale / 100.0
+    assert np.array_equal(pred[~ties], pred_ref[~ties]), f"{(pred[~ties] != pred_ref[~ties]).sum()} label mismatches"
+    assert ties.mean() < 2e-3
+    np.testing.assert_allclose(conf[~ties], conf_ref[~ties], rtol=1e-4)
+    tab = native.table_to_numpy(table)
+    assert np.array_equal(tab, orc.bin_table(conf, pred, case.labels, thr)), "fused binning != binning of its own outputs"
+    assert abs(tm.ece_from_table(tab) - ece_ref) < 1e-5
+    counts = tab[:, 0].astype(np.int64); folded = counts[:10].copy(); folded[9] += counts[10]
+    moved = np.abs(folded - counts_ref).sum()
+    assert moved <= 2 * (near_edge(conf_ref, 10).sum() + ties.sum()), (folded, counts_ref)
+    return pred, conf
+
+
+@pytest.mark.parametrize("name", ["eurosat", "sun397_l14", "imagenet", "openvocab"])
+def test_fused_scoring_matches_reference(cuda_lib, name, golden, synth_case):
+    g, case = golden(name), synth_case(name)
+    check_scoring(case, g["cc_k5"], g["dac_pred"], g["dac_conf"], g["dac_gap"], float(g["dac_ece10"]), g["dac_counts10"])
+    check_scoring(case, None, g["nodac_pred"], g["nodac_conf"], g["nodac_gap"], float(g["nodac_ece10"]), g["nodac_counts10"])
+
+
+@pytest.mark.parametrize("n,c,d", [(1, 1, 64), (127, 255, 64), (129, 257, 128), (1000, 513, 512), (300, 40, 1024), (4096, 3000, 640)])
+def test_fused_scoring_ragged_shapes_fp16_and_bf16(cuda_lib, n, c, d):
+    for dtype, rounding in ((torch.bfloat16, synth.round_to_bf16), (torch.float16, synth.round_to_fp16)):
+        case = synth.make_case("ragged", n, c, max(1, c // 2), d, 5, 0.3, seed=n + c, rounding=rounding)
+        cc = (0.95 + 0.05 * np.random.default_rng(c).random(c)).astype(np.float32)
+        pref, cref, gap = orc.score_chain(case.img, case.txt_tuned, cc, case.logit_scale)
+        ece_ref = orc.ece(cref, pref, case.labels, 10)
+        counts = np.histogram(cref, np.linspace(0, 1, 11))[0]
+        check_scoring(case, cc, pref, cref, gap, ece_ref, counts, dtype)
+
+
+def test_end_to_end_pipeline_and_host_path(cuda_lib, golden, synth_case):
+    g, case = golden("imagenet"), synth_case("imagenet")
+    scorer = pipeline.CalibratedScorer.from_dac(case.base_zs, case.txt_zs, case.base_tuned, case.txt_tuned, k=5,
+                                                logit_scale=case.logit_scale, n_bins=10)
+    pred, conf = scorer.score(case.img, case.labels)
+    s = scorer.summary()
+    assert s["n"] == len(case.labels)
+    assert abs(s["ece"] - float(g["dac_ece10"])) < 1e-5 and abs(s["mce"] - float(g["dac_mce10"])) < 1e-5
+    assert abs(s["accuracy"] - float(g["dac_acc"])) < 1e-4 and abs(s["confidence"] - float(g["dac_mean_conf"])) < 1e-5
+    assert abs(metrics.AdaptiveECE(conf, pred, dev(case.labels), 10) - float(g["dac_ace10"])) < 1e-5
+    # host inputs, chunked H2D overlapped with compute: identical table
+    device_table = s["table"].copy()
+    scorer.reset()
+    host = torch.from_numpy(case.img).to(torch.bfloat16).pin_memory()
+    scorer.accumulate_host(host, torch.from_numpy(case.labels).pin_memory(), chunk_rows=8192)
+    assert np.array_equal(scorer.reduced_table(), device_table)
+    # shards add up exactly (what the multi-GPU all-reduce relies on)
+    scorer.reset()
+    for r in range(3):
+        lo, hi = pipeline.shard_bounds(len(case.labels), r, 3)
+        scorer.score(case.img[lo:hi], case.labels[lo:hi])
+    assert np.array_equal(scorer.reduced_table(), device_table)
+
+
+# ----------------------------------------------------------------------------- K5
+@pytest.mark.parametrize("n,c,d,t", [(200, 37, 128, 4.6052), (1000, 500, 512, 4.0), (64, 1000, 768, 5.0)])
+def test_temperature_scaling_loss_and_gradient(cuda_lib, n, c, d, t):
+    case = synth.make_case("ts", n, c, max(1, c // 2), d, 5, 0.3, seed=n)
+    loss, grad = tempscaling.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t)
+    lref, gref = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t)
+    assert abs(loss - lref) <= 1e-4 * max(1.0, abs(lref)), (loss, lref)
+    assert abs(grad - gref) <= 1e-4 * max(1.0, abs(gref)), (grad, gref)
+
+
+def test_fit_logit_scale_reduces_loss_and_checkpoint_roundtrip(cuda_lib, tmp_path):
+    case = synth.make_case("tsfit", 512, 100, 50, 512, 5, 0.3, seed=21)
+    l0, _ = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, tempscaling.INIT_LOG_SCALE)
+    t = tempscaling.fit_logit_scale(case.img, case.txt_tuned, case.labels, epochs=5)
+    l1, g1 = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t)
+    assert l1 < l0
+    tempscaling.save_logit_scale(str(tmp_path), t, 5)
+    assert abs(tempscaling.load_logit_scale(str(tmp_path), 5) - t) < 1e-6
+    learner = tempscaling.ScaleLearner(None, torch.float32)
+    assert abs(float(learner()) - np.exp(4.6052)) < 1e-3 and list(learner.state_dict()) == ["logit_scale"]
+
+
+# ----------------------------------------------------------------------------- errors
+def test_bad_arguments_fail_loudly(cuda_lib):
+    with pytest.raises(ValueError):
+        native.score_fused(torch.zeros(8, 100, dtype=torch.bfloat16, device="cuda"),
+                           torch.zeros(8, 100, dtype=torch.bfloat16, device="cuda"))         # D not a multiple of 64
+    with pytest.raises(ValueError):
+        native.score_fused(torch.zeros(8, 64, dtype=torch.float32, device="cuda"),
+                           torch.zeros(8, 64, dtype=torch.float32, device="cuda"))           # fp32 operands
+    with pytest.raises(ValueError):
+        native.knn_l2(torch.zeros(4, 64, device="cuda"), torch.zeros(4, 64, device="cuda"), 99)
+    with pytest.raises(Exception):
+        native.bin_stats(torch.zeros(4), torch.zeros(4, dtype=torch.int32), torch.zeros(4, dtype=torch.int64), [0.5])

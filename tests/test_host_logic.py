@@ -1,0 +1,110 @@
+"""CPU: host-side logic of the product (table arithmetic, quantile edges, sharding, ABI surface).
+No CUDA compute is called here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from clip_calibration_b200 import table_math as tm
+from clip_calibration_b200 import pipeline, synth
+from oracle import cpu_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_table_composition_reproduces_reference_metrics(golden):
+    g = golden("metric_edge_cases")
+    for name in g["names"]:
+        conf, pred, gt = g[f"{name}_conf"], g[f"{name}_pred"], g[f"{name}_gt"]
+        for nb in (10, 15):
+            tab = orc.bin_table(conf, pred, gt, tm.uniform_thresholds(nb))
+            assert abs(tm.ece_from_table(tab) - float(g[f"{name}_ece{nb}"])) < 1e-7, name
+            assert abs(tm.mce_from_table(tab) - float(g[f"{name}_mce{nb}"])) < 1e-7, name
+            assert tm.total_count(tab) == len(conf)
+            assert abs(tm.accuracy(tab) - np.mean(pred == gt)) < 1e-15
+
+
+@pytest.mark.parametrize("name", ["eurosat", "sun397_l14", "imagenet"])
+def test_table_composition_on_golden_cases(name, golden, synth_case):
+    g, case = golden(name), synth_case(name)
+    for tag in ("dac", "nodac"):
+        conf, pred = g[f"{tag}_conf"], g[f"{tag}_pred"]
+        tab = orc.bin_table(conf, pred, case.labels, tm.uniform_thresholds(10))
+        assert abs(tm.ece_from_table(tab) - float(g[f"{tag}_ece10"])) < 1e-7
+        assert abs(tm.mce_from_table(tab) - float(g[f"{tag}_mce10"])) < 1e-7
+        counts = tab[:, 0].astype(np.int64)
+        folded = counts[:10].copy(); folded[9] += counts[10]
+        assert np.array_equal(folded, g[f"{tag}_counts10"])
+        # adaptive bins through the same table machinery
+        thr = orc.quantile_edges(conf, 10)[1:-1]
+        assert abs(tm.sum_of_gaps(orc.bin_table(conf, pred, case.labels, thr)) - float(g[f"{tag}_ace10"])) < 1e-7
+
+
+def test_quantile_ranks_match_numpy_percentile():
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        n = int(rng.integers(1, 4000))
+        nb = int(rng.choice([2, 5, 10, 15]))
+        x = rng.random(n).astype(np.float32)
+        if trial % 3 == 0:
+            x = (np.round(x * 10) / 10).astype(np.float32)
+        xs = np.sort(x)
+        for method in ("averaged_inverted_cdf", "linear", "inverted_cdf"):
+            lo, hi, gamma = tm.quantile_ranks(n, nb, method)
+            mine = tm.lerp_like_numpy(xs[lo], xs[hi], gamma)
+            ref = np.asarray(np.percentile(x, np.linspace(0, 100, nb + 1), method=method), np.float64)
+            assert np.array_equal(mine, ref), (n, nb, method)
+            assert np.array_equal(tm.edges_from_order_stats(xs[lo], xs[hi], gamma),
+                                  orc.quantile_edges(x, nb, method))
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 128, 1000003):
+        for world in (1, 2, 3, 8):
+            cuts = [pipeline.shard_bounds(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_bf16_rounding_matches_torch():
+    import torch
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(100000).astype(np.float32)
+    assert np.array_equal(synth.round_to_bf16(x), torch.from_numpy(x).bfloat16().float().numpy())
+
+
+def test_library_exports_every_declared_symbol():
+    from clip_calibration_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "ccal.h")).read()
+    declared = set(re.findall(r"CCAL_API\s+[\w\s\*]+?\b(ccal_\w+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.ccal_version.restype = ctypes.c_int
+    assert lib.ccal_version() == 100
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    from clip_calibration_b200 import _lib, native
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.CcalError):
+        native.score_fused(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(4, 64, dtype=torch.bfloat16))
+    lib = _lib.load()
+    assert lib.ccal_check_device() != 0 and _lib.last_error()
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "clip_calibration_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "cpu_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f

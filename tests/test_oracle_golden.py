@@ -1,0 +1,73 @@
+"""CPU: the oracle restatement against the golden vectors produced by the real reference
+functions (oracle/make_golden.py).  Integer / index results must be identical; float results
+within the stated tolerances (MKL thread count and ISA may move last digits of the GEMM)."""
+import numpy as np
+import pytest
+
+from oracle import cpu_oracle as orc
+
+
+@pytest.mark.parametrize("name", ["eurosat", "sun397_l14", "imagenet", "openvocab"])
+def test_score_chain_matches_reference(name, golden, synth_case):
+    g, case = golden(name), synth_case(name)
+    k = 5
+    cc = g[f"cc_k{k}"]
+    for tag, ccx in (("dac", cc), ("nodac", None)):
+        pred, conf, gap = orc.score_chain(case.img, case.txt_tuned, ccx, case.logit_scale)
+        ties = g[f"{tag}_gap"] <= 4e-5
+        assert np.array_equal(pred[~ties], g[f"{tag}_pred"][~ties])
+        np.testing.assert_allclose(conf[~ties], g[f"{tag}_conf"][~ties], rtol=2e-5)
+        assert abs(orc.ece(conf, pred, case.labels, 10) - float(g[f"{tag}_ece10"])) < 1e-6
+
+
+@pytest.mark.parametrize("name,ks", [("eurosat", (5,)), ("sun397_l14", (1, 5, 10)), ("imagenet", (5,)), ("openvocab", (5,))])
+def test_dac_fit_matches_reference(name, ks, golden, synth_case):
+    g, case = golden(name), synth_case(name)
+    for k in ks:
+        sel = g[f"fit_sel_k{k}"]
+        if name == "imagenet":
+            sel = sel[::8]
+        cc, iz, it, dz, dt = orc.dac_fit(case.base_zs, case.txt_zs[sel], case.base_tuned, case.txt_tuned[sel], k)
+        ref_sel = np.searchsorted(g[f"fit_sel_k{k}"], sel)
+        assert np.array_equal(cc, g[f"cc_k{k}"][sel])
+        assert np.array_equal(it, g[f"knn_idx_tuned_k{k}"][ref_sel])
+        assert np.array_equal(iz, g[f"knn_idx_zs_k{k}"][ref_sel])
+    # base classes are calibrated with multiplier exactly 1 (self distance 0 < 0.05)
+    assert np.all(g[f"cc_k{ks[0]}"][: int(g["n_base"])] == 1.0)
+
+
+def test_metric_edge_cases(golden):
+    g = golden("metric_edge_cases")
+    for name in g["names"]:
+        conf, pred, gt = g[f"{name}_conf"], g[f"{name}_pred"], g[f"{name}_gt"]
+        for nb in (10, 15):
+            assert abs(orc.ece(conf, pred, gt, nb) - float(g[f"{name}_ece{nb}"])) < 1e-12, name
+            assert abs(orc.mce(conf, pred, gt, nb) - float(g[f"{name}_mce{nb}"])) < 3e-8, name
+            assert abs(orc.adaptive_ece(conf, pred, gt, nb) - float(g[f"{name}_ace{nb}"])) < 3e-8, name
+
+
+def test_reference_quirk_conf_equal_one():
+    # the 1.0 sample is in no bin mean but in the last bin's weight
+    assert orc.ece(np.array([1.0, 0.5], np.float32), np.array([0, 0]), np.array([0, 0]), 10) == 0.25
+
+
+def test_proximity_and_piece(golden):
+    from clip_calibration_b200 import synth
+    g = golden("proximity_piece")
+    case = synth.make_case("prox", 600, 40, 20, 512, 5, 0.3, seed=3)
+    val = synth.make_case("proxval", 300, 40, 20, 512, 5, 0.3, seed=4).img
+    np.testing.assert_allclose(orc.knn_dists(val, case.img, 5), g["knn"], rtol=1e-6)
+    np.testing.assert_allclose(orc.knn_dists(val, val, 5, drop_self=True), g["knn_self"], rtol=1e-6, atol=1e-7)
+    prox = np.exp(-np.mean(g["knn"], axis=-1))
+    for nb in (10, 5):
+        assert abs(orc.piece(g["conf"], prox, g["pred"], g["labels"], nb, 10) - float(g[f"piece{nb}"])) < 3e-8
+
+
+def test_ts_loss_grad_against_finite_difference():
+    from clip_calibration_b200 import synth
+    case = synth.make_case("ts", 200, 37, 19, 128, 5, 0.3, seed=5)
+    t = 4.6052
+    loss, grad = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t)
+    lp, _ = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t + 1e-5)
+    lm, _ = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t - 1e-5)
+    assert abs((lp - lm) / 2e-5 - grad) < 1e-6 * max(1.0, abs(grad))
