@@ -246,7 +246,7 @@ def ts_loss_and_grad(img, txt, labels, log_scale: float):
     t = torch.tensor(float(log_scale), dtype=torch.float64, requires_grad=True)
     loss = torch.nn.functional.cross_entropy(t.exp() * a @ b.t(), y)
     loss.backward()
-    return float(loss), float(t.grad)
+    return float(loss.detach()), float(t.grad)
 
 
 # --------------------------------------------------------------------------------------
