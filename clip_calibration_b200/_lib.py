@@ -26,6 +26,8 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p]),
     "ccal_knn_l2": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
                             c_void_p]),
+    "ccal_knn_l2_exhaustive": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p]),
     "ccal_dac_fit": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ccal_dac_predict_logits": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),

@@ -62,16 +62,118 @@ bin_stats_kernel(const ConfT* __restrict__ conf, const PredT* __restrict__ pred,
   }
 }
 
+
+// Fast path (float confidences, 1-D table with <= kFastCells bins - every ECE/MCE/ACE call):
+// every lane owns a private column of cells in shared memory, [warp][bin][lane], so the update
+// is a plain 16-byte load / add / store: no atomics, no bank conflicts (a quarter warp of 128-bit
+// accesses covers all 32 banks whatever the bins are), no inter-lane dependency chains.  Each
+// thread streams 4 consecutive images per iteration with 128-bit loads.
+constexpr int kFastCells = 16;
+constexpr int kFastWarps = kBinThreads / 32;
+
+struct __align__(16) LaneCell {
+  unsigned int count;
+  unsigned int correct;
+  unsigned long long sum_fx;
+};
+
+template <typename PredT>
+__global__ void __launch_bounds__(kBinThreads)
+bin_stats_fast_kernel(const float* __restrict__ conf, const PredT* __restrict__ pred,
+                      const long long* __restrict__ gt, long long n,
+                      const __grid_constant__ Thr32 thr, int n_thr, unsigned long long* __restrict__ table) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  LaneCell* cells = reinterpret_cast<LaneCell*>(smem_raw);           // [kFastWarps][n_cells][32]
+  __shared__ float s_thr[kFastCells];
+  const int n_cells = n_thr + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < kFastWarps * n_cells * 32; i += blockDim.x) cells[i] = LaneCell{0u, 0u, 0ull};
+  if (threadIdx.x < kFastCells) s_thr[threadIdx.x] = threadIdx.x < n_thr ? thr.t[threadIdx.x] : 0.f;
+  __syncthreads();
+  LaneCell* mine = cells + (size_t)warp * n_cells * 32 + lane;
+
+  auto add = [&](float x, long long p, long long g) {
+    int b = 0;
+    for (int j = 0; j < n_thr; ++j) b += (x >= s_thr[j]) ? 1 : 0;
+    LaneCell c = mine[b * 32];
+    c.count += 1u;
+    c.correct += (p == g) ? 1u : 0u;
+    c.sum_fx += conf_to_fx(x);
+    mine[b * 32] = c;
+  };
+
+  const long long n4 = n / 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(conf) | reinterpret_cast<uintptr_t>(pred) |
+                         reinterpret_cast<uintptr_t>(gt)) & 15) == 0;
+  long long done = 0;
+  if (aligned) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 x = __ldcs(reinterpret_cast<const float4*>(conf) + i);
+      long long p[4];
+      if (sizeof(PredT) == 4) {
+        const int4 q = __ldcs(reinterpret_cast<const int4*>(pred) + i);
+        p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
+      } else {
+        const longlong2 q0 = __ldcs(reinterpret_cast<const longlong2*>(pred) + 2 * i);
+        const longlong2 q1 = __ldcs(reinterpret_cast<const longlong2*>(pred) + 2 * i + 1);
+        p[0] = q0.x; p[1] = q0.y; p[2] = q1.x; p[3] = q1.y;
+      }
+      const longlong2 g0 = __ldcs(reinterpret_cast<const longlong2*>(gt) + 2 * i);
+      const longlong2 g1 = __ldcs(reinterpret_cast<const longlong2*>(gt) + 2 * i + 1);
+      add(x.x, p[0], g0.x); add(x.y, p[1], g0.y); add(x.z, p[2], g1.x); add(x.w, p[3], g1.y);
+    }
+    done = n4 * 4;
+  }
+  for (long long i = done + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    add(conf[i], (long long)pred[i], gt[i]);
+  __syncthreads();
+  // column sums: one warp per cell, lanes stride over the kFastWarps*32 private copies
+  for (int cell = warp; cell < n_cells; cell += kFastWarps) {
+    unsigned long long cnt = 0, cor = 0, sm = 0;
+    for (int w = 0; w < kFastWarps; ++w) {
+      const LaneCell c = cells[((size_t)w * n_cells + cell) * 32 + lane];
+      cnt += c.count; cor += c.correct; sm += c.sum_fx;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+      cor += __shfl_xor_sync(0xffffffffu, cor, off);
+      sm += __shfl_xor_sync(0xffffffffu, sm, off);
+    }
+    if (lane == 0 && cnt) {
+      atomicAdd(&table[3 * cell + 0], cnt);
+      atomicAdd(&table[3 * cell + 1], cor);
+      atomicAdd(&table[3 * cell + 2], sm);
+    }
+  }
+}
+
 // order-preserving key of a non-negative float = its bit pattern
+// Keys of values in [2^-31, 2) - every confidence / proximity that matters - fall in the 4096-key
+// window [0x3000, 0x4000): that window is privatised per CTA in shared memory (warp-aggregated
+// shared atomics), everything else goes straight to global atomics.
+constexpr unsigned kWinLo = 0x3000u, kWinSize = 0x1000u;
+
 __global__ void __launch_bounds__(kBinThreads)
 radix_hist_level0(const float* __restrict__ keys, long long n, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int win[kWinSize];
+  for (int i = threadIdx.x; i < (int)kWinSize; i += blockDim.x) win[i] = 0u;
+  __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const unsigned key = __float_as_uint(keys[i]) >> 16;
+    const unsigned key = __float_as_uint(__ldcs(keys + i)) >> 16;
     // confidences cluster (e.g. saturated 1.0): one atomic per distinct key per warp
     const unsigned peers = __match_any_sync(__activemask(), key);
-    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[key], (unsigned)__popc(peers));
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) {
+      const unsigned w = key - kWinLo;
+      if (w < kWinSize) atomicAdd(&win[w], (unsigned)__popc(peers));
+      else atomicAdd(&hist[key], (unsigned)__popc(peers));
+    }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (int)kWinSize; i += blockDim.x)
+    if (win[i]) atomicAdd(&hist[kWinLo + i], win[i]);
 }
 
 __global__ void __launch_bounds__(kBinThreads)
@@ -124,9 +226,25 @@ extern "C" int ccal_bin_stats(const void* conf, int conf_f64, const void* pred, 
     t2.t[i] = i < n_thr2 ? ceil_to_f32(thresholds2_host[i]) : 0.0f;
   }
   const int n_cells = (n_thr + 1) * (n_thr2 + 1);
+  const long long* g = reinterpret_cast<const long long*>(gt);
+  if (!conf_f64 && n_thr2 == 0 && n_cells <= kFastCells) {
+    // float keys: compare against ceil_f32(threshold) (equivalent to the double comparison)
+    Thr32 tf;
+    for (int i = 0; i < CCAL_MAX_THRESHOLDS; ++i) tf.t[i] = i < n_thr ? ceil_to_f32(thresholds_host[i]) : 0.0f;
+    const size_t fsmem = sizeof(LaneCell) * kFastWarps * n_cells * 32;
+    const int fgrid = grid_for((n + 3) / 4, kBinThreads, 4);
+    if (pred_i64) {
+      CCAL_CUDA_OK(cudaFuncSetAttribute(bin_stats_fast_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      bin_stats_fast_kernel<long long><<<fgrid, kBinThreads, fsmem, stream>>>((const float*)conf, (const long long*)pred, g, (long long)n, tf, n_thr, table);
+    } else {
+      CCAL_CUDA_OK(cudaFuncSetAttribute(bin_stats_fast_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+      bin_stats_fast_kernel<int><<<fgrid, kBinThreads, fsmem, stream>>>((const float*)conf, (const int*)pred, g, (long long)n, tf, n_thr, table);
+    }
+    CCAL_CUDA_OK(cudaGetLastError());
+    return CCAL_OK;
+  }
   const size_t smem = sizeof(BinCell) * n_cells + sizeof(double) * n_thr + sizeof(float) * n_thr2;
   const int grid = grid_for(n, kBinThreads, 8);
-  const long long* g = reinterpret_cast<const long long*>(gt);
 #define CCAL_LAUNCH_BIN(CT, PT)                                                                   \
   bin_stats_kernel<CT, PT><<<grid, kBinThreads, smem, stream>>>(                                  \
       (const CT*)conf, (const PT*)pred, g, (long long)n, t1, n_thr, key2, t2, n_thr2, table)

@@ -32,6 +32,10 @@ int fail(int code, const char* fmt, ...);
 
 int num_sms();
 
+// TMA descriptor of a [rows, d] row-major 16-bit matrix (dtype CCAL_BF16 / CCAL_F16), box =
+// {64 features, box_rows}, 128-byte swizzle, zero fill out of range (defined in score_fused.cu).
+int make_map(CUtensorMap* map, const void* base, long long rows, int d, int box_rows, int dtype);
+
 // Thresholds are given as doubles (np.linspace edges are float64 and np.digitize compares
 // in double).  For a float key x and a double threshold t:  x >= t  <=>  x >= ceil_f32(t),
 // the smallest float32 that is >= t.  So the device compares floats only.

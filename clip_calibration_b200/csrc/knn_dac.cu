@@ -37,9 +37,12 @@ __device__ __forceinline__ void list_insert(TopList& e, float d, int i, int cap,
   }
 }
 
+// List mode (qlist != NULL): only the *qcount query rows named in qlist are processed (the rows the
+// tensor-core filter could not prove, csrc/knn_tc.cu); CTAs loop over 64-query tiles.
 __global__ void __launch_bounds__(256)
-knn_l2_kernel(const float* __restrict__ ref, const float* __restrict__ query, long long nr, long long nq,
-              int d, int k, int drop_first, float* __restrict__ dist_out, int* __restrict__ idx_out) {
+knn_l2_kernel(const float* __restrict__ ref, const float* __restrict__ query, long long nr, long long nq_all,
+              int d, int k, int drop_first, float* __restrict__ dist_out, int* __restrict__ idx_out,
+              const int* __restrict__ qlist, const int* __restrict__ qcount) {
   __shared__ __align__(16) float Qs[kChunk][kPad];
   __shared__ __align__(16) float Rs[kChunk][kPad];
   __shared__ float Dt[kTile][kTile + 1];
@@ -49,8 +52,11 @@ knn_l2_kernel(const float* __restrict__ ref, const float* __restrict__ query, lo
   const int warp = tid >> 5;
   const int ty = tid >> 4, tx = tid & 15;           // 16 x 16 threads, 4 x 4 outputs each
   const int ld_row = tid >> 2, ld_col = (tid & 3) * 4;
-  const long long q0 = (long long)blockIdx.x * kTile;
   const int cap = min((long long)(k + (drop_first ? 1 : 0)), nr);   // list length actually used
+  const long long nq = qlist ? (long long)*qcount : nq_all;
+  for (long long q0 = (long long)blockIdx.x * kTile; q0 < nq; q0 += (long long)gridDim.x * kTile) {
+  // global row of this thread's staged query row (list mode gathers)
+  const long long ld_q = (q0 + ld_row < nq) ? (qlist ? (long long)qlist[q0 + ld_row] : q0 + ld_row) : -1;
 
   TopList lists[kRowsPerWarp];
 #pragma unroll
@@ -67,7 +73,7 @@ knn_l2_kernel(const float* __restrict__ ref, const float* __restrict__ query, lo
       float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), rv = qv;
       const int dc = d0 + ld_col;
       if (dc < d) {                                     // d % 4 == 0 is required by the host
-        if (q0 + ld_row < nq) qv = *reinterpret_cast<const float4*>(query + (q0 + ld_row) * d + dc);
+        if (ld_q >= 0) qv = *reinterpret_cast<const float4*>(query + ld_q * d + dc);
         if (r0 + ld_row < nr) rv = *reinterpret_cast<const float4*>(ref + (r0 + ld_row) * d + dc);
       }
       __syncthreads();                                   // previous chunk fully consumed
@@ -125,14 +131,17 @@ knn_l2_kernel(const float* __restrict__ ref, const float* __restrict__ query, lo
   const int skip = drop_first ? 1 : 0;
 #pragma unroll
   for (int r = 0; r < kRowsPerWarp; ++r) {
-    const long long q = q0 + warp * kRowsPerWarp + r;
+    const long long ql = q0 + warp * kRowsPerWarp + r;
     // entry `lane` of the list goes to output slot lane - skip
     const int slot = lane - skip;
-    if (q < nq && slot >= 0 && slot < k) {
+    if (ql < nq && slot >= 0 && slot < k) {
+      const long long q = qlist ? (long long)qlist[ql] : ql;
       const bool have = lane < cap;
       if (dist_out) dist_out[q * k + slot] = have ? lists[r].d : CUDART_INF_F;
       if (idx_out) idx_out[q * k + slot] = have ? lists[r].i : -1;
     }
+  }
+  __syncthreads();                                   // Dt / Qs / Rs are reused by the next query tile
   }
 }
 
@@ -167,14 +176,27 @@ __global__ void dac_map_kernel(const float* __restrict__ dist_zs, const float* _
   class_conf[i] = ((double)b[0] < 0.05) ? 1.0f : __fdiv_rn(fs_score, zs_score);
 }
 
-static int launch_knn(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k, int drop_first,
-                      float* dist_out, int32_t* idx_out, cudaStream_t stream) {
-  const long long grid = (nq + kTile - 1) / kTile;
-  CCAL_REQUIRE(grid <= 2147483647ll, "ccal_knn_l2: too many query rows");
+int launch_knn_exact(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k, int drop_first,
+                     float* dist_out, int32_t* idx_out, const int* qlist, const int* qcount, cudaStream_t stream) {
+  long long grid = (nq + kTile - 1) / kTile;
+  const long long cap = (long long)num_sms() * 4;
+  if (qlist != nullptr && grid > cap) grid = cap;     // list mode: usually (almost) nothing to do
+  if (grid > 2147483647ll) grid = 2147483647ll;
   knn_l2_kernel<<<(int)grid, 256, 0, stream>>>(ref, query, (long long)nr, (long long)nq, d, k, drop_first,
-                                               dist_out, idx_out);
+                                               dist_out, idx_out, qlist, qcount);
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
+}
+
+int knn_l2_tensor(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k, int drop_first,
+                  float* dist_out, int32_t* idx_out, cudaStream_t stream);
+
+// tensor-core filter + exact verification when the problem is big enough to amortise it
+static int launch_knn(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k, int drop_first,
+                      float* dist_out, int32_t* idx_out, cudaStream_t stream) {
+  const bool tc_ok = (d % 64 == 0) && d <= 1024 && nr >= 256 && nq >= 256 && nr * nq >= (1ll << 20);
+  if (tc_ok) return knn_l2_tensor(ref, query, nr, nq, d, k, drop_first, dist_out, idx_out, stream);
+  return launch_knn_exact(ref, query, nr, nq, d, k, drop_first, dist_out, idx_out, nullptr, nullptr, stream);
 }
 
 }  // namespace ccal
@@ -191,6 +213,17 @@ extern "C" int ccal_knn_l2(const float* ref, const float* query, int64_t nr, int
   CCAL_REQUIRE(ref && query, "ccal_knn_l2: NULL input");
   CCAL_REQUIRE(((uintptr_t)ref % 16 == 0) && ((uintptr_t)query % 16 == 0), "ccal_knn_l2: 16-byte alignment required");
   return launch_knn(ref, query, nr, nq, d, k, drop_first, dist_out, idx_out, (cudaStream_t)stream);
+}
+
+extern "C" int ccal_knn_l2_exhaustive(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k,
+                                      int drop_first, float* dist_out, int32_t* idx_out, ccal_stream_t stream) {
+  CCAL_REQUIRE(nr >= 1 && nq >= 0 && nr < 2147483647ll, "ccal_knn_l2_exhaustive: bad row counts");
+  CCAL_REQUIRE(d >= 4 && d % 4 == 0, "ccal_knn_l2_exhaustive: d must be a positive multiple of 4 (got %d)", d);
+  CCAL_REQUIRE(k >= 1 && k <= CCAL_MAX_K, "ccal_knn_l2_exhaustive: k must be in 1..%d (got %d)", CCAL_MAX_K, k);
+  if (nq == 0) return CCAL_OK;
+  CCAL_REQUIRE(ref && query, "ccal_knn_l2_exhaustive: NULL input");
+  CCAL_REQUIRE(((uintptr_t)ref % 16 == 0) && ((uintptr_t)query % 16 == 0), "ccal_knn_l2_exhaustive: 16-byte alignment required");
+  return launch_knn_exact(ref, query, nr, nq, d, k, drop_first, dist_out, idx_out, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int ccal_dac_fit(const float* base_zs, const float* cur_zs, const float* base_tuned,

@@ -1,10 +1,13 @@
 // K4: drop-ins that work on MATERIALISED logits [n, c] (fp32, row-major).
-//   dac_predict_logits : logits[i,:] *= class_conf[argmax_j logits[i,j]]     (in place)
-//   logits_confidence  : pred_i, conf_i = max softmax(class_conf[pred_i] * logits[i,:])
-// HBM-bound: each row is read from HBM once (the second sweep over the row hits L1/L2) and,
-// for the in-place variant, written once.  Algorithmic bytes per image: 8*c (in place) or
-// 4*c (+8 out) for the confidence variant.
-// One warp per row while c <= 2048, one 256-thread CTA per row above that.
+//   dac_predict_logits  : logits[i,:] *= class_conf[argmax_j logits[i,j]]            (in place)
+//   logits_confidence   : pred_i, conf_i = max softmax(class_conf[pred_i] * logits[i,:])
+//   dac_softmax_logits  : logits[i,:] <- softmax(class_conf[pred_i] * logits[i,:])     (in place)
+//   row_argmax          : first argmax + row maximum
+// HBM-bound: each row is read from HBM once (the later sweeps over the row hit L1/L2) and, for
+// the in-place variants, written once.  Algorithmic bytes per image: 8*c in place, 4*c (+8 out)
+// for the read-only variants.
+// GROUP threads cooperate on one row: 1 (c <= 16), 8 (c <= 128), 32 (c <= 2048), 256 = the CTA.
+// 128-bit loads/stores whenever rows are 16-byte aligned (c % 4 == 0).
 #include "ccal_common.cuh"
 
 #include <math_constants.h>
@@ -22,9 +25,10 @@ __device__ __forceinline__ MaxIdx better(MaxIdx a, MaxIdx b) {
   return a;
 }
 
-__device__ __forceinline__ MaxIdx warp_argmax(MaxIdx m) {
+template <int GROUP>
+__device__ __forceinline__ MaxIdx group_argmax(MaxIdx m) {
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
+  for (int off = (GROUP > 32 ? 32 : GROUP) / 2; off > 0; off >>= 1) {
     MaxIdx o;
     o.v = __shfl_xor_sync(0xffffffffu, m.v, off);
     o.i = __shfl_xor_sync(0xffffffffu, m.i, off);
@@ -33,15 +37,15 @@ __device__ __forceinline__ MaxIdx warp_argmax(MaxIdx m) {
   return m;
 }
 
-__device__ __forceinline__ float warp_sum(float s) {
+template <int GROUP>
+__device__ __forceinline__ float group_sum(float s) {
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  for (int off = (GROUP > 32 ? 32 : GROUP) / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   return s;
 }
 
 enum RowOp { kScaleInPlace = 0, kConfidence = 1, kSoftmaxInPlace = 2, kArgmaxOnly = 3 };
 
-// GROUP = threads cooperating on one row (32 = a warp, 256 = the CTA).  OP selects the operation.
 template <int GROUP, int OP>
 __global__ void __launch_bounds__(256)
 logits_rows_kernel(float* __restrict__ logits, const float* __restrict__ class_conf, long long n, int c,
@@ -54,17 +58,32 @@ logits_rows_kernel(float* __restrict__ logits, const float* __restrict__ class_c
   const int t = threadIdx.x % GROUP;          // index inside the row group
   const long long group0 = (long long)blockIdx.x * kGroupsPerCta + threadIdx.x / GROUP;
   const long long group_stride = (long long)gridDim.x * kGroupsPerCta;
-  // uniform trip count per CTA so that the __syncthreads below are safe
-  const long long rows_per_sweep = group_stride;
-  const long long sweeps = (n + rows_per_sweep - 1) / rows_per_sweep;
+  // uniform trip count per CTA so that the collectives / __syncthreads below are safe
+  const long long sweeps = (n + group_stride - 1) / group_stride;
+  const bool vec = (c % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) && GROUP > 1;
+  const int c4 = c >> 2;
   for (long long sweep = 0; sweep < sweeps; ++sweep) {
     const long long row = group0 + sweep * group_stride;
     const bool live = row < n;
     float* x = logits + (live ? row : 0) * (long long)c;
+    float4* x4 = reinterpret_cast<float4*>(x);
+
+    // ---- sweep 1: first argmax
     MaxIdx m{-CUDART_INF_F, 0x7fffffff};
-    if (live)
-      for (int j = t; j < c; j += GROUP) m = better(m, MaxIdx{x[j], j});
-    m = warp_argmax(m);
+    if (live) {
+      if (vec) {
+#pragma unroll 4
+        for (int j = t; j < c4; j += GROUP) {
+          const float4 v = x4[j];
+          m = better(m, MaxIdx{v.x, 4 * j}); m = better(m, MaxIdx{v.y, 4 * j + 1});
+          m = better(m, MaxIdx{v.z, 4 * j + 2}); m = better(m, MaxIdx{v.w, 4 * j + 3});
+        }
+      } else {
+#pragma unroll 4
+        for (int j = t; j < c; j += GROUP) m = better(m, MaxIdx{x[j], j});
+      }
+    }
+    m = group_argmax<GROUP>(m);
     if (GROUP > 32) {
       if (lane == 0) s_red[warp] = m;
       __syncthreads();
@@ -75,58 +94,99 @@ logits_rows_kernel(float* __restrict__ logits, const float* __restrict__ class_c
     }
     const int pred = m.i;
     const float cc = (live && class_conf) ? class_conf[pred] : 1.0f;
+
     if (OP == kArgmaxOnly) {
       if (live && t == 0) {
         if (pred_out) pred_out[row] = pred;
         if (conf_out) conf_out[row] = m.v;
       }
-    } else if (OP == kScaleInPlace) {
+      continue;
+    }
+    if (OP == kScaleInPlace) {
       if (live) {
         // fp32 multiply, exactly what `logits *= class_confidences[pred][:, None]` does
-        for (int j = t; j < c; j += GROUP) x[j] = __fmul_rn(x[j], cc);
+        if (vec) {
+#pragma unroll 4
+          for (int j = t; j < c4; j += GROUP) {
+            float4 v = x4[j];
+            v.x = __fmul_rn(v.x, cc); v.y = __fmul_rn(v.y, cc); v.z = __fmul_rn(v.z, cc); v.w = __fmul_rn(v.w, cc);
+            x4[j] = v;
+          }
+        } else {
+          for (int j = t; j < c; j += GROUP) x[j] = __fmul_rn(x[j], cc);
+        }
         if (t == 0 && pred_out) pred_out[row] = pred;
       }
-    } else {
-      const float mcc = __fmul_rn(m.v, cc);
-      float s = 0.f;
-      if (live)
-        for (int j = t; j < c; j += GROUP) s += expf(__fsub_rn(__fmul_rn(x[j], cc), mcc));
-      s = warp_sum(s);
-      if (GROUP > 32) {
-        if (lane == 0) s_sum[warp] = s;
-        __syncthreads();
-        s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s += s_sum[w];
-        __syncthreads();
-      }
-      if (OP == kSoftmaxInPlace && live) {
-        // probabilities in place: exp(cc*x - cc*max) / sum  (scipy softmax of the DAC-scaled row)
-        for (int j = t; j < c; j += GROUP) x[j] = __fdiv_rn(expf(__fsub_rn(__fmul_rn(x[j], cc), mcc)), s);
-      }
-      if (live && t == 0) {
-        if (pred_out) pred_out[row] = pred;
-        if (conf_out) conf_out[row] = 1.0f / s;
+      continue;
+    }
+
+    // ---- sweep 2: sum of exp of the DAC-scaled, max-shifted row (scipy softmax arithmetic)
+    const float mcc = __fmul_rn(m.v, cc);
+    // probabilities that are RETURNED use the accurate expf; the confidence-only variant sums
+    // thousands of terms and uses the MUFU-based __expf (relative error ~2e-6)
+    auto ex = [&](float v) {
+      const float a = __fsub_rn(__fmul_rn(v, cc), mcc);
+      return OP == kConfidence ? __expf(a) : expf(a);
+    };
+    float s = 0.f;
+    if (live) {
+      if (vec) {
+#pragma unroll 4
+        for (int j = t; j < c4; j += GROUP) {
+          const float4 v = x4[j];
+          s += (ex(v.x) + ex(v.y)) + (ex(v.z) + ex(v.w));
+        }
+      } else {
+        for (int j = t; j < c; j += GROUP) s += ex(x[j]);
       }
     }
+    s = group_sum<GROUP>(s);
+    if (GROUP > 32) {
+      if (lane == 0) s_sum[warp] = s;
+      __syncthreads();
+      s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += s_sum[w];
+      __syncthreads();
+    }
+    if (OP == kSoftmaxInPlace && live) {
+      if (vec) {
+#pragma unroll 4
+        for (int j = t; j < c4; j += GROUP) {
+          float4 v = x4[j];
+          v.x = __fdiv_rn(ex(v.x), s); v.y = __fdiv_rn(ex(v.y), s); v.z = __fdiv_rn(ex(v.z), s); v.w = __fdiv_rn(ex(v.w), s);
+          x4[j] = v;
+        }
+      } else {
+        for (int j = t; j < c; j += GROUP) x[j] = __fdiv_rn(ex(x[j]), s);
+      }
+    }
+    if (live && t == 0) {
+      if (pred_out) pred_out[row] = pred;
+      if (conf_out) conf_out[row] = 1.0f / s;
+    }
   }
+}
+
+template <int GROUP, int OP>
+static int launch_group(float* logits, const float* class_conf, int64_t n, int c, int* pred_out, float* conf_out,
+                        cudaStream_t stream) {
+  const long long rows_per_cta = 256 / GROUP;
+  const long long want = (n + rows_per_cta - 1) / rows_per_cta;
+  const long long cap = (long long)num_sms() * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  logits_rows_kernel<GROUP, OP><<<grid, 256, 0, stream>>>(logits, class_conf, (long long)n, c, pred_out, conf_out);
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
 }
 
 template <int OP>
 static int launch_rows(float* logits, const float* class_conf, int64_t n, int c, int* pred_out, float* conf_out,
                        cudaStream_t stream) {
-  const int sms = num_sms();
-  if (c <= 2048) {
-    long long want = (n + 7) / 8;
-    int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
-    logits_rows_kernel<32, OP><<<grid, 256, 0, stream>>>(logits, class_conf, (long long)n, c, pred_out, conf_out);
-  } else {
-    long long want = n;
-    int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
-    logits_rows_kernel<256, OP><<<grid, 256, 0, stream>>>(logits, class_conf, (long long)n, c, pred_out, conf_out);
-  }
-  CCAL_CUDA_OK(cudaGetLastError());
-  return CCAL_OK;
+  if (c <= 16) return launch_group<1, OP>(logits, class_conf, n, c, pred_out, conf_out, stream);
+  if (c <= 128) return launch_group<8, OP>(logits, class_conf, n, c, pred_out, conf_out, stream);
+  if (c <= 2048) return launch_group<32, OP>(logits, class_conf, n, c, pred_out, conf_out, stream);
+  return launch_group<256, OP>(logits, class_conf, n, c, pred_out, conf_out, stream);
 }
 
 }  // namespace ccal

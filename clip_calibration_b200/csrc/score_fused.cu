@@ -367,7 +367,7 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // [rows, d] row-major 16-bit matrix, box = {64 features, box_rows}, 128-byte swizzle, zero OOB fill
-static int make_map(CUtensorMap* map, const void* base, long long rows, int d, int box_rows, int dtype) {
+int make_map(CUtensorMap* map, const void* base, long long rows, int d, int box_rows, int dtype) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(CCAL_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};

@@ -133,7 +133,9 @@ def ts_loss_grad(img: torch.Tensor, txt: torch.Tensor, labels: torch.Tensor, log
 # --------------------------------------------------------------------------------------
 # K1  kNN + DAC fit
 # --------------------------------------------------------------------------------------
-def knn_l2(ref: torch.Tensor, query: torch.Tensor, k: int, drop_first: bool = False):
+def knn_l2(ref: torch.Tensor, query: torch.Tensor, k: int, drop_first: bool = False, exhaustive: bool = False):
+    """k nearest `ref` rows of every `query` row: (dist [nq,k] ascending, idx [nq,k]).  Large problems
+    run a tcgen05 GEMM filter + exact fp32 verification; `exhaustive=True` forces the plain exact scan."""
     lib = _lib.load()
     ref = _need_cuda("ref", ref, torch.float32, 2)
     query = _need_cuda("query", query, torch.float32, 2)
@@ -143,8 +145,9 @@ def knn_l2(ref: torch.Tensor, query: torch.Tensor, k: int, drop_first: bool = Fa
     dist = torch.empty((nq, k), dtype=torch.float32, device=ref.device)
     idx = torch.empty((nq, k), dtype=torch.int32, device=ref.device)
     with torch.cuda.device(ref.device):
-        rc = lib.ccal_knn_l2(_ptr(ref), _ptr(query), ref.shape[0], nq, d, int(k), int(bool(drop_first)),
-                             _ptr(dist), _ptr(idx), _stream())
+        fn = lib.ccal_knn_l2_exhaustive if exhaustive else lib.ccal_knn_l2
+        rc = fn(_ptr(ref), _ptr(query), ref.shape[0], nq, d, int(k), int(bool(drop_first)),
+                _ptr(dist), _ptr(idx), _stream())
     _lib.check(rc, "ccal_knn_l2")
     _count(1 if nq else 0)
     return dist, idx
@@ -171,7 +174,7 @@ def dac_fit(base_zs, cur_zs, base_tuned, cur_tuned, k: int):
         rc = lib.ccal_dac_fit(_ptr(base_zs), _ptr(cur_zs), _ptr(base_tuned), _ptr(cur_tuned), b, c, d, int(k),
                               _ptr(cc), _ptr(iz), _ptr(it), _ptr(dz), _ptr(dt), _stream())
     _lib.check(rc, "ccal_dac_fit")
-    _count(3 if c else 0)
+    _count(11 if c else 0)   # 2 x (split, split, gemm filter, verify, redo) + map on the tensor-core path
     return cc, iz, it, dz, dt
 
 

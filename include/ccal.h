@@ -101,6 +101,10 @@ CCAL_API int ccal_ts_loss_grad(const void* img, const void* txt, const int64_t* 
  */
 CCAL_API int ccal_knn_l2(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k,
                 int drop_first, float* dist_out, int32_t* idx_out, ccal_stream_t stream);
+/* Same contract, always the exhaustive fp32 scan (ccal_knn_l2 switches to a tcgen05 GEMM filter +
+ * exact verification for large problems and uses this scan for the rows it cannot prove). */
+CCAL_API int ccal_knn_l2_exhaustive(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k,
+                int drop_first, float* dist_out, int32_t* idx_out, ccal_stream_t stream);
 
 /* ccal_dac_fit = DistanseAwareCalibration.fit (distanse_aware_calibration.py:13-46):
  * class_conf_out[i] = 1 if nearest tuned distance < 0.05 else

@@ -109,6 +109,45 @@ def test_dac_fit_k_larger_than_base_and_duplicates(cuda_lib):
     assert np.array_equal(dac.knn_indices_zs.cpu().numpy()[:, :3], iz)        # ties -> lowest index first
 
 
+@pytest.mark.parametrize("nr,nq,d,k,drop", [(1000, 5000, 512, 5, False), (3000, 3000, 768, 10, True), (257, 4100, 64, 16, False),
+                                             (10000, 2048, 512, 1, False)])
+def test_knn_tensor_core_filter_equals_exhaustive_scan(cuda_lib, nr, nq, d, k, drop):
+    """ccal_knn_l2 (tcgen05 GEMM filter + exact verification + exhaustive redo of unproven rows) must
+    return what the exhaustive fp32 scan returns."""
+    g = torch.Generator(device="cuda").manual_seed(nr + nq)
+    ref = torch.nn.functional.normalize(torch.randn(nr, d, device="cuda", generator=g) + 2.0, dim=-1)
+    qry = ref if drop else torch.nn.functional.normalize(torch.randn(nq, d, device="cuda", generator=g) + 2.0, dim=-1)
+    d_tc, i_tc = native.knn_l2(ref, qry, k, drop)
+    d_ex, i_ex = native.knn_l2(ref, qry, k, drop, exhaustive=True)
+    torch.testing.assert_close(d_tc, d_ex, rtol=2e-6, atol=2e-7)
+    diff = i_tc != i_ex
+    assert diff.float().mean() < 1e-3
+    if diff.any():                                         # only where two distances coincide to rounding
+        assert float((d_tc[diff] - d_ex[diff]).abs().max()) <= 1e-6
+    # oracle spot check (reference formula on the CPU)
+    rows = slice(0, 64)
+    ref_d = orc.knn_dists(ref.cpu().numpy(), qry[rows].cpu().numpy(), k, drop_self=drop)
+    np.testing.assert_allclose(d_tc[rows].cpu().numpy(), ref_d, rtol=3e-6, atol=3e-7)
+
+
+def test_knn_tensor_core_falls_back_on_ties_and_wild_norms(cuda_lib):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    base = torch.nn.functional.normalize(torch.randn(40, 128, device="cuda", generator=g), dim=-1)
+    ref = base.repeat_interleave(32, dim=0).contiguous()           # every row 32 times: ties across the cut
+    qry = torch.nn.functional.normalize(torch.randn(2000, 128, device="cuda", generator=g), dim=-1)
+    d_tc, i_tc = native.knn_l2(ref, qry, 5)
+    d_ex, i_ex = native.knn_l2(ref, qry, 5, exhaustive=True)
+    assert torch.equal(i_tc, i_ex) and torch.equal(d_tc, d_ex)     # unproven rows are redone by the same scan
+    # un-normalised rows with norms spread over 3 decades
+    scale = torch.logspace(-1, 2, 1500, device="cuda")[:, None]
+    ref2 = torch.randn(1500, 256, device="cuda", generator=g) * scale
+    qry2 = torch.randn(1024, 256, device="cuda", generator=g) * 3.0
+    d_tc, i_tc = native.knn_l2(ref2, qry2, 5)
+    d_ex, i_ex = native.knn_l2(ref2, qry2, 5, exhaustive=True)
+    torch.testing.assert_close(d_tc, d_ex, rtol=3e-6, atol=1e-6)
+    assert (i_tc != i_ex).float().mean() < 1e-3
+
+
 def test_proximity_knn(cuda_lib, golden):
     g = golden("proximity_piece")
     case = synth.make_case("prox", 600, 40, 20, 512, 5, 0.3, seed=3)
