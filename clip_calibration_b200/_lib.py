@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint32, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_longlong, c_uint32, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libccal.so")
@@ -18,6 +18,7 @@ MAX_K = 16
 SIGNATURES = {
     "ccal_version": (c_int, []),
     "ccal_last_error": (c_char_p, []),
+    "ccal_launch_count": (c_longlong, []),
     "ccal_check_device": (c_int, []),
     "ccal_score_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int,

@@ -236,9 +236,11 @@ extern "C" int ccal_bin_stats(const void* conf, int conf_f64, const void* pred, 
     if (pred_i64) {
       CCAL_CUDA_OK(cudaFuncSetAttribute(bin_stats_fast_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       bin_stats_fast_kernel<long long><<<fgrid, kBinThreads, fsmem, stream>>>((const float*)conf, (const long long*)pred, g, (long long)n, tf, n_thr, table);
+      note_launch();
     } else {
       CCAL_CUDA_OK(cudaFuncSetAttribute(bin_stats_fast_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
       bin_stats_fast_kernel<int><<<fgrid, kBinThreads, fsmem, stream>>>((const float*)conf, (const int*)pred, g, (long long)n, tf, n_thr, table);
+      note_launch();
     }
     CCAL_CUDA_OK(cudaGetLastError());
     return CCAL_OK;
@@ -253,6 +255,7 @@ extern "C" int ccal_bin_stats(const void* conf, int conf_f64, const void* pred, 
   } else {
     if (pred_i64) CCAL_LAUNCH_BIN(float, long long); else CCAL_LAUNCH_BIN(float, int);
   }
+  note_launch();
 #undef CCAL_LAUNCH_BIN
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
@@ -269,11 +272,13 @@ extern "C" int ccal_radix_hist(const float* keys, int64_t n, int level, const ui
   const int grid = grid_for(n, kBinThreads, 8);
   if (level == 0) {
     radix_hist_level0<<<grid, kBinThreads, 0, stream>>>(keys, (long long)n, hist);
+    note_launch();
   } else {
     CCAL_REQUIRE(n_prefix >= 1 && n_prefix <= 64 && prefixes_host, "ccal_radix_hist: 1..64 prefixes required");
     Prefixes pf;
     for (int i = 0; i < 64; ++i) pf.p[i] = i < n_prefix ? prefixes_host[i] : 0xFFFFFFFFu;
     radix_hist_level1<<<grid, kBinThreads, 0, stream>>>(keys, (long long)n, pf, n_prefix, hist);
+    note_launch();
   }
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;

@@ -4,6 +4,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <atomic>
+
 namespace ccal {
 
 char* error_buffer() {
@@ -18,6 +20,9 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+static std::atomic<long long> g_kernel_launches{0};
+void note_launch(int n) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int num_sms() {
   static thread_local int cached_dev = -1, cached = 0;
@@ -41,6 +46,8 @@ float ceil_to_f32(double t) {
 }  // namespace ccal
 
 extern "C" int ccal_version(void) { return CCAL_VERSION; }
+
+extern "C" long long ccal_launch_count(void) { return ccal::g_kernel_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* ccal_last_error(void) { return ccal::error_buffer(); }
 

@@ -31,6 +31,7 @@ int fail(int code, const char* fmt, ...);
   } while (0)
 
 int num_sms();
+void note_launch(int n = 1);   // process-wide count of kernels this library launched
 
 // TMA descriptor of a [rows, d] row-major 16-bit matrix (dtype CCAL_BF16 / CCAL_F16), box =
 // {64 features, box_rows}, 128-byte swizzle, zero fill out of range (defined in score_fused.cu).

@@ -184,6 +184,7 @@ int launch_knn_exact(const float* ref, const float* query, int64_t nr, int64_t n
   if (grid > 2147483647ll) grid = 2147483647ll;
   knn_l2_kernel<<<(int)grid, 256, 0, stream>>>(ref, query, (long long)nr, (long long)nq, d, k, drop_first,
                                                dist_out, idx_out, qlist, qcount);
+  note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
 }
@@ -244,6 +245,7 @@ extern "C" int ccal_dac_fit(const float* base_zs, const float* cur_zs, const flo
   if (rc) return rc;
   const int kk = k < b ? k : b;
   dac_map_kernel<<<(c + 127) / 128, 128, 0, stream>>>(knn_dist_zs_out, knn_dist_tuned_out, c, k, kk, class_conf_out);
+  note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
 }

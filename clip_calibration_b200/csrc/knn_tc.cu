@@ -291,6 +291,7 @@ static int run_tc(const float* ref, const float* query, int64_t nr, int64_t nq, 
                   const float* rhn, const unsigned int* rmax, __nv_bfloat16* qhi, __nv_bfloat16* qlo, float* qhn, int* cand, float* cut,
                   int* redo_list, int* redo_count, cudaStream_t stream) {
   split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(query, nq, d, qhi, qlo, qhn, nullptr);
+  note_launch();
   CUtensorMap mqh, mql, mrh, mrl;
   int rc;
   if ((rc = make_map(&mqh, qhi, nq, d, kTcBlockM, CCAL_BF16))) return rc;
@@ -309,9 +310,11 @@ static int run_tc(const float* ref, const float* query, int64_t nr, int64_t nq, 
   CCAL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = num_sms();
   kern<<<p.n_row_tiles < sms ? p.n_row_tiles : sms, kTcThreads, smem, stream>>>(mqh, mql, mrh, mrl, p);
+  note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   knn_verify_kernel<KP><<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(ref, query, nr, nq, d, k, drop_first, cand, cut, qhn,
                                                                       rmax, dist_out, idx_out, redo_list, redo_count);
+  note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return launch_knn_exact(ref, query, nr, nq, d, k, drop_first, dist_out, idx_out, redo_list, redo_count, stream);
 }
@@ -351,6 +354,7 @@ int knn_l2_tensor(const float* ref, const float* query, int64_t nr, int64_t nq, 
   unsigned int* rmax = (unsigned int*)(ws + o_rmax);
   cudaMemsetAsync(rmax, 0, sizeof(unsigned int), stream);
   split_rows_kernel<<<(unsigned)((nr + 7) / 8), 256, 0, stream>>>(ref, nr, d, rhi, rlo, rhn, rmax);
+  note_launch();
   int rc = CCAL_OK;
   for (int64_t q0 = 0; q0 < nq && rc == CCAL_OK; q0 += chunk) {
     const int64_t m = (nq - q0) < chunk ? (nq - q0) : chunk;

@@ -176,6 +176,7 @@ static int launch_group(float* logits, const float* class_conf, int64_t n, int c
   const long long cap = (long long)num_sms() * 8;
   const int grid = (int)(want < cap ? want : cap);
   logits_rows_kernel<GROUP, OP><<<grid, 256, 0, stream>>>(logits, class_conf, (long long)n, c, pred_out, conf_out);
+  note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
 }

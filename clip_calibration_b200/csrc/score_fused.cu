@@ -387,6 +387,7 @@ static int launch_variant(const CUtensorMap& mi, const CUtensorMap& mt, const Sc
   auto kern = score_fused_kernel<kResident, kMode>;
   CCAL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kThreads, smem, stream>>>(mi, mt, p, thr);
+  note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
 }
@@ -479,6 +480,7 @@ extern "C" int ccal_ts_loss_grad(const void* img, const void* txt, const int64_t
   int rc = run_fused(1, img, txt, n, c, d, dtype, p, thr, stream);
   if (rc) return rc;
   ts_reduce_kernel<<<1, 1024, 0, stream>>>(row_ws, (long long)n, out2);
+  note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
 }

@@ -16,16 +16,9 @@ from . import _lib
 from ._lib import CCAL_BF16, CCAL_F16, FX_SHIFT, MAX_K, MAX_THRESHOLDS
 
 _DTYPES = {torch.bfloat16: CCAL_BF16, torch.float16: CCAL_F16}
-_launches = 0     # kernels launched by this library in this process (bench.py reports it)
-
-
 def launch_count() -> int:
-    return _launches
-
-
-def _count(n: int) -> None:
-    global _launches
-    _launches += n
+    """Kernels launched by libccal.so in this process (counted inside the library at each launch site)."""
+    return int(_lib.load().ccal_launch_count())
 
 
 def _stream() -> int:
@@ -102,7 +95,6 @@ def score_fused(img: torch.Tensor, txt: torch.Tensor, class_conf: Optional[torch
                                   _ptr(labels) if table is not None else None, thr_arr, n_thr,
                                   _ptr(table), _stream())
     _lib.check(rc, "ccal_score_fused")
-    _count(1)
     return pred, conf, rowmax
 
 
@@ -126,7 +118,6 @@ def ts_loss_grad(img: torch.Tensor, txt: torch.Tensor, labels: torch.Tensor, log
         rc = lib.ccal_ts_loss_grad(_ptr(img), _ptr(txt), _ptr(labels), float(log_scale), n, c, d,
                                    _DTYPES[img.dtype], _ptr(ws), _ptr(out), _stream())
     _lib.check(rc, "ccal_ts_loss_grad")
-    _count(2)
     return out
 
 
@@ -149,7 +140,6 @@ def knn_l2(ref: torch.Tensor, query: torch.Tensor, k: int, drop_first: bool = Fa
         rc = fn(_ptr(ref), _ptr(query), ref.shape[0], nq, d, int(k), int(bool(drop_first)),
                 _ptr(dist), _ptr(idx), _stream())
     _lib.check(rc, "ccal_knn_l2")
-    _count(1 if nq else 0)
     return dist, idx
 
 
@@ -174,7 +164,6 @@ def dac_fit(base_zs, cur_zs, base_tuned, cur_tuned, k: int):
         rc = lib.ccal_dac_fit(_ptr(base_zs), _ptr(cur_zs), _ptr(base_tuned), _ptr(cur_tuned), b, c, d, int(k),
                               _ptr(cc), _ptr(iz), _ptr(it), _ptr(dz), _ptr(dt), _stream())
     _lib.check(rc, "ccal_dac_fit")
-    _count(11 if c else 0)   # 2 x (split, split, gemm filter, verify, redo) + map on the tensor-core path
     return cc, iz, it, dz, dt
 
 
@@ -194,7 +183,6 @@ def dac_predict_logits_(logits: torch.Tensor, class_conf: torch.Tensor) -> torch
     with torch.cuda.device(logits.device):
         rc = lib.ccal_dac_predict_logits(_ptr(logits), _ptr(class_conf), n, c, _ptr(pred), _stream())
     _lib.check(rc, "ccal_dac_predict_logits")
-    _count(1 if n else 0)
     return pred
 
 
@@ -209,7 +197,6 @@ def logits_confidence(logits: torch.Tensor, class_conf: Optional[torch.Tensor] =
     with torch.cuda.device(logits.device):
         rc = lib.ccal_logits_confidence(_ptr(logits), _ptr(class_conf), n, c, _ptr(pred), _ptr(conf), _stream())
     _lib.check(rc, "ccal_logits_confidence")
-    _count(1 if n else 0)
     return pred, conf
 
 
@@ -226,7 +213,6 @@ def dac_softmax_logits_(logits: torch.Tensor, class_conf: Optional[torch.Tensor]
     with torch.cuda.device(logits.device):
         rc = lib.ccal_dac_softmax_logits(_ptr(logits), _ptr(class_conf), n, c, _ptr(pred), _ptr(conf), _stream())
     _lib.check(rc, "ccal_dac_softmax_logits")
-    _count(1 if n else 0)
     return pred, conf
 
 
@@ -240,7 +226,6 @@ def row_argmax(values: torch.Tensor):
     with torch.cuda.device(values.device):
         rc = lib.ccal_row_argmax(_ptr(values), n, c, _ptr(pred), _ptr(mx), _stream())
     _lib.check(rc, "ccal_row_argmax")
-    _count(1 if n else 0)
     return pred, mx
 
 
@@ -275,7 +260,6 @@ def bin_stats(conf: torch.Tensor, pred: torch.Tensor, gt: torch.Tensor, threshol
                                 int(pred.dtype == torch.int64), _ptr(gt), n, thr, n_thr,
                                 _ptr(key2), thr2, n_thr2, _ptr(table), _stream())
     _lib.check(rc, "ccal_bin_stats")
-    _count(1 if n else 0)
     return table
 
 
@@ -290,7 +274,6 @@ def radix_hist(keys: torch.Tensor, level: int, prefixes: Optional[Sequence[int]]
     with torch.cuda.device(keys.device):
         rc = lib.ccal_radix_hist(_ptr(keys), keys.numel(), int(level), pf, n_pf, _ptr(hist), _stream())
     _lib.check(rc, "ccal_radix_hist")
-    _count(1 if keys.numel() else 0)
     return hist
 
 

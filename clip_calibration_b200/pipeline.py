@@ -44,7 +44,7 @@ class CalibratedScorer:
         self.logit_scale = float(logit_scale)
         self.n_bins = int(n_bins)
         self.thresholds = tm.uniform_thresholds(self.n_bins)
-        self.group = group
+        self.group = group          # None = default process group (if initialised); False = never reduce
         self.table = native.new_table(self.n_bins, device=self.device)
         self._copy_stream = None
 
@@ -129,8 +129,8 @@ class CalibratedScorer:
         """The bin table summed over all ranks of `group` (one NCCL all-reduce of
         3*(n_bins+1) int64 on the compute stream), as a host uint64 array."""
         t = self.table
-        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                      and torch.distributed.get_world_size() > 1):
+        if self.group is not False and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size(self.group) > 1:
             t = t.clone()
             torch.distributed.all_reduce(t, group=self.group)
         return native.table_to_numpy(t)

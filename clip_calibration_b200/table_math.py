@@ -45,6 +45,21 @@ def mean_confidence(table) -> float:
     return float(sm.sum() / cnt.sum())
 
 
+def reliability_bins(table) -> dict:
+    """Per-bin accuracy / mean confidence / count of an (n+1)-bin uniform table, i.e. the data behind
+    the reference's reliability diagram (tools/plot.py:8-71), overflow bin folded into the last bar."""
+    cnt, cor, sm = _cols(table)
+    n = len(cnt) - 1
+    cnt, cor, sm = cnt.copy(), cor.copy(), sm.copy()
+    cnt[n - 1] += cnt[n]; cor[n - 1] += cor[n]; sm[n - 1] += sm[n]
+    cnt, cor, sm = cnt[:n], cor[:n], sm[:n]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        acc = np.where(cnt > 0, cor / cnt, 0.0)
+        conf = np.where(cnt > 0, sm / cnt, 0.0)
+    edges = np.linspace(0, 1, n + 1)
+    return {"edges": edges, "count": cnt.astype(np.int64), "accuracy": acc, "confidence": conf, "gap": conf - acc}
+
+
 def ece_from_table(table) -> np.float64:
     """Reference ECE from the (n+1)-bin table built with uniform_thresholds(n).
 

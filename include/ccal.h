@@ -55,6 +55,9 @@ typedef void* ccal_stream_t;
 CCAL_API int ccal_version(void);
 CCAL_API const char* ccal_last_error(void);
 
+/* Number of CUDA kernels this library has launched in this process (monotonic). */
+CCAL_API long long ccal_launch_count(void);
+
 /* 0 if the current device can run this library (compute capability 10.x). */
 CCAL_API int ccal_check_device(void);
 

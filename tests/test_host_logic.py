@@ -108,3 +108,33 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "cpu_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_handoff_formats_roundtrip(tmp_path):
+    import torch
+    from clip_calibration_b200 import handoff
+    p = handoff.base_features_path("EuroSAT", "CoOp", 16, "ViT-B/16".replace("/", "-"), 1, root=str(tmp_path))
+    assert p.endswith("base_features/EuroSAT/CoOp/shots16/ViT-B-16/base/seed1/base_features.pt")
+    rng = np.random.default_rng(0)
+    handoff.save_base_features(p, rng.random((6, 5)), torch.rand(6, 8), rng.random((5, 8)), np.arange(6), rng.random((6, 5)))
+    d = handoff.load_base_features(p)
+    assert set(handoff.BASE_FEATURE_KEYS) <= set(d) and d["val_image_features"].shape == (6, 8)
+    kp = handoff.knndist_path("EuroSAT", "CoOp", 16, "ViT-B-16", "new", 1, 5, root=str(tmp_path))
+    os.makedirs(os.path.dirname(kp)); np.save(kp, rng.random((4, 5)).astype(np.float32))
+    kd = handoff.load_or_compute_knn_dists(kp, None, None, 5)           # cached file wins, no GPU touched
+    assert kd.shape == (4, 5) and handoff.proximity_from_knn(kd).shape == (4,)
+    acc = handoff.FeatureAccumulator(torch.float32)
+    acc.process(torch.ones(3, 4), torch.arange(3)); acc.process(torch.zeros(2, 4), torch.arange(2))
+    img, lab = acc.tensors()
+    assert img.shape == (5, 4) and lab.dtype == torch.int64 and len(acc) == 5
+
+
+def test_reliability_bins_from_table():
+    rng = np.random.default_rng(2)
+    conf = np.where(rng.random(5000) < 0.1, 1.0, rng.random(5000)).astype(np.float32)
+    pred, gt = rng.integers(0, 3, 5000), rng.integers(0, 3, 5000)
+    rb = tm.reliability_bins(orc.bin_table(conf, pred, gt, tm.uniform_thresholds(10)))
+    assert np.array_equal(rb["count"], np.histogram(conf, np.linspace(0, 1, 11))[0])
+    sel = conf >= 0.9
+    assert abs(rb["accuracy"][9] - np.mean(pred[sel] == gt[sel])) < 1e-12
+    assert abs(rb["confidence"][9] - np.mean(conf[sel].astype(np.float64))) < 1e-9
