@@ -20,6 +20,7 @@
 #include "sm100_ptx.cuh"
 
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace ccal {
 
@@ -114,7 +115,12 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&raw)[32], int nv, flo
   if (kMode == 1) wsum += w0 + w1;
 }
 
-template <bool kResident, int kMode>
+// kCtas = 1: one CTA per 128-row image tile (tcgen05 cta_group::1).
+// kCtas = 2: a CTA PAIR (2-CTA cluster, cta_group::2) per 256-row tile: each CTA keeps its own 128 image
+//            rows resident and loads only HALF of every text tile (128 classes); the pair's leader issues
+//            256x256x16 MMAs that read both halves.  Halves the L2->SMEM text traffic and the SMEM->tensor
+//            B traffic per flop - on a power-capped B200 that is what buys throughput.
+template <int kCtas, bool kResident, int kMode>
 __global__ void __launch_bounds__(kThreads, 1)
 score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__ CUtensorMap map_txt,
                    const __grid_constant__ ScoreParams p, const __grid_constant__ ThrBlock thr) {
@@ -124,12 +130,19 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
   const uint32_t ctl_end = ptx::smem_u32(smem_dyn) + kCtlBytes;
   const uint32_t op_base = (ctl_end + 1023u) & ~1023u;
   unsigned char* op_ptr = smem_dyn + (op_base - ptx::smem_u32(smem_dyn));
+  constexpr int kBBytes = kBTileBytes / kCtas;           // text bytes this CTA loads per stage
+  constexpr int kBRows = kBlockN / kCtas;                // classes this CTA loads per text tile
+  constexpr int kTileRows = kBlockM * kCtas;             // image rows per (pair) tile
   // resident: [A slab 0..kblocks) then ring of B tiles; streaming: ring of {A slab, B tile}
-  const uint32_t stage_bytes = kResident ? kBTileBytes : (kASlabBytes + kBTileBytes);
+  const uint32_t stage_bytes = kResident ? kBBytes : (kASlabBytes + kBBytes);
   unsigned char* ring_ptr = op_ptr + (kResident ? p.kblocks * kASlabBytes : 0);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (kCtas == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit = (kCtas == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = (int)gridDim.x / kCtas;
 
   // ------------------------------------------------------------------ one-time setup
   if (warp == 0 && lane == 0) {
@@ -137,19 +150,19 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
     ptx::prefetch_tensormap(&map_txt);
     for (int i = 0; i < kMaxKBlocks; ++i) { ptx::mbar_init(&ctl->a_full[i], 1); ptx::mbar_init(&ctl->a_empty[i], 1); }
     for (int i = 0; i < kMaxStages; ++i) { ptx::mbar_init(&ctl->b_full[i], 1); ptx::mbar_init(&ctl->b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&ctl->tmem_full[i], 1); ptx::mbar_init(&ctl->tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&ctl->tmem_full[i], 1); ptx::mbar_init(&ctl->tmem_empty[i], 4 * kCtas); }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(&ctl->tmem_base, kTmemCols);
-    ptx::tmem_relinquish();
+    if (kCtas == 2) { ptx::tmem_alloc_2sm(&ctl->tmem_base, kTmemCols); ptx::tmem_relinquish_2sm(); }
+    else { ptx::tmem_alloc(&ctl->tmem_base, kTmemCols); ptx::tmem_relinquish(); }
   }
   for (int i = threadIdx.x; i <= CCAL_MAX_THRESHOLDS; i += kThreads) {
     ctl->cells[i] = BinCell{0u, 0u, 0ull};
     ctl->thr[i] = (i < p.n_thr) ? thr.t[i] : CUDART_INF_F;
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) ptx::cluster_sync_all(); else __syncthreads();   // peer barriers initialised before any remote signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
@@ -157,74 +170,94 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
   const int KB = p.kblocks;
 
   if (warp == 0) {
-    // ================================================================ TMA producer
-    if (lane == 0) {
-      uint32_t it = 0;
-      uint32_t ti = 0;
-      for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x, ++ti) {
-        const int row0 = tile * kBlockM;
-        for (int pass = 0; pass < 2; ++pass) {
-          for (int nt = 0; nt < NT; ++nt) {
-            for (int kb = 0; kb < KB; ++kb, ++it) {
-              const uint32_t stage = it % (uint32_t)p.stages;
-              const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
-              unsigned char* sp = ring_ptr + (size_t)stage * stage_bytes;
+    // ================================================================ TMA producer (whole warp loops, one
+    // elected lane issues; keeping the control flow warp-uniform keeps the issue path short)
+    uint32_t stage = 0, phase = 0, ti = 0;
+    for (int tile = unit; tile < p.n_row_tiles; tile += n_units, ++ti) {
+      const int row0 = tile * kTileRows + (int)rank * kBlockM;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int nt = 0; nt < NT; ++nt) {
+          const int col0 = nt * kBlockN + (int)rank * kBRows;
+          const bool load_a = kResident && pass == 0 && nt == 0;
+          for (int kb = 0; kb < KB; ++kb) {
+            unsigned char* sp = ring_ptr + (size_t)stage * stage_bytes;
+            // slab kb of the previous row tile must have been consumed by its last MMA
+            if (load_a) ptx::mbar_wait(&ctl->a_empty[kb], (ti & 1u) ^ 1u);
+            ptx::mbar_wait(&ctl->b_empty[stage], phase ^ 1u);
+            if (ptx::elect_one()) {
               if (kResident) {
-                if (pass == 0 && nt == 0) {
-                  // slab kb of the previous row tile must have been consumed by its last MMA
-                  ptx::mbar_wait(&ctl->a_empty[kb], (ti & 1u) ^ 1u);
-                  ptx::mbar_arrive_expect_tx(&ctl->a_full[kb], kASlabBytes);
-                  ptx::tma_load_2d(op_ptr + (size_t)kb * kASlabBytes, &map_img, &ctl->a_full[kb], kb * kBlockK, row0,
-                                   ptx::kEvictFirst);
+                if (load_a) {
+                  if (leader) ptx::mbar_arrive_expect_tx(&ctl->a_full[kb], kASlabBytes * kCtas);
+                  if (kCtas == 2) ptx::tma_load_2d_2sm(op_ptr + (size_t)kb * kASlabBytes, &map_img, &ctl->a_full[kb], kb * kBlockK, row0, ptx::kEvictFirst);
+                  else ptx::tma_load_2d(op_ptr + (size_t)kb * kASlabBytes, &map_img, &ctl->a_full[kb], kb * kBlockK, row0, ptx::kEvictFirst);
                 }
-                ptx::mbar_wait(&ctl->b_empty[stage], ph ^ 1u);
-                ptx::mbar_arrive_expect_tx(&ctl->b_full[stage], kBTileBytes);
-                ptx::tma_load_2d(sp, &map_txt, &ctl->b_full[stage], kb * kBlockK, nt * kBlockN, ptx::kEvictLast);
+                if (leader) ptx::mbar_arrive_expect_tx(&ctl->b_full[stage], kBBytes * kCtas);
+                if (kCtas == 2) ptx::tma_load_2d_2sm(sp, &map_txt, &ctl->b_full[stage], kb * kBlockK, col0, ptx::kEvictLast);
+                else ptx::tma_load_2d(sp, &map_txt, &ctl->b_full[stage], kb * kBlockK, col0, ptx::kEvictLast);
               } else {
-                ptx::mbar_wait(&ctl->b_empty[stage], ph ^ 1u);
-                ptx::mbar_arrive_expect_tx(&ctl->b_full[stage], kASlabBytes + kBTileBytes);
-                ptx::tma_load_2d(sp, &map_img, &ctl->b_full[stage], kb * kBlockK, row0, ptx::kEvictNormal);
-                ptx::tma_load_2d(sp + kASlabBytes, &map_txt, &ctl->b_full[stage], kb * kBlockK, nt * kBlockN,
-                                 ptx::kEvictLast);
+                if (leader) ptx::mbar_arrive_expect_tx(&ctl->b_full[stage], (kASlabBytes + kBBytes) * kCtas);
+                if (kCtas == 2) {
+                  ptx::tma_load_2d_2sm(sp, &map_img, &ctl->b_full[stage], kb * kBlockK, row0, ptx::kEvictNormal);
+                  ptx::tma_load_2d_2sm(sp + kASlabBytes, &map_txt, &ctl->b_full[stage], kb * kBlockK, col0, ptx::kEvictLast);
+                } else {
+                  ptx::tma_load_2d(sp, &map_img, &ctl->b_full[stage], kb * kBlockK, row0, ptx::kEvictNormal);
+                  ptx::tma_load_2d(sp + kASlabBytes, &map_txt, &ctl->b_full[stage], kb * kBlockK, col0, ptx::kEvictLast);
+                }
               }
             }
+            __syncwarp();
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer
-    if (lane == 0) {
-      uint32_t it = 0, acc_it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x, ++ti) {
+    // ================================================================ MMA issuer (pair leader only; whole warp
+    // waits, one elected lane issues: ~4 MMAs + 1-2 commits per 64-feature block must fit in 512 cycles)
+    if (leader) {
+      uint32_t stage = 0, phase = 0, acc_it = 0, ti = 0;
+      const uint32_t ring_base = op_base + (kResident ? (uint32_t)KB * kASlabBytes : 0u);
+      for (int tile = unit; tile < p.n_row_tiles; tile += n_units, ++ti) {
         for (int pass = 0; pass < 2; ++pass) {
           for (int nt = 0; nt < NT; ++nt, ++acc_it) {
             const uint32_t as = acc_it & 1u;
             const uint32_t aph = (acc_it >> 1) & 1u;
-            ptx::mbar_wait(&ctl->tmem_empty[as], aph ^ 1u);      // epilogue has drained this stage
+            ptx::mbar_wait(&ctl->tmem_empty[as], aph ^ 1u);      // epilogue(s) have drained this stage
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * kBlockN;
-            for (int kb = 0; kb < KB; ++kb, ++it) {
-              const uint32_t stage = it % (uint32_t)p.stages;
-              const uint32_t ph = (it / (uint32_t)p.stages) & 1u;
-              const uint32_t sp = op_base + (kResident ? (uint32_t)KB * kASlabBytes : 0u) + stage * stage_bytes;
-              if (kResident && pass == 0 && nt == 0) ptx::mbar_wait(&ctl->a_full[kb], ti & 1u);
-              ptx::mbar_wait(&ctl->b_full[stage], ph);
+            const bool first_use_of_a = kResident && pass == 0 && nt == 0;
+            const bool last_use_of_a = kResident && pass == 1 && nt == NT - 1;
+            for (int kb = 0; kb < KB; ++kb) {
+              const uint32_t sp = ring_base + stage * stage_bytes;
+              if (first_use_of_a) ptx::mbar_wait(&ctl->a_full[kb], ti & 1u);
+              ptx::mbar_wait(&ctl->b_full[stage], phase);
               ptx::tc_fence_after();
-              const uint32_t a_addr = kResident ? op_base + (uint32_t)kb * kASlabBytes : sp;
-              const uint32_t b_addr = kResident ? sp : sp + kASlabBytes;
-              const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
-              const uint64_t b_desc = ptx::make_kmajor_sw128_desc(b_addr);
+              if (ptx::elect_one()) {
+                const uint32_t a_addr = kResident ? op_base + (uint32_t)kb * kASlabBytes : sp;
+                const uint32_t b_addr = kResident ? sp : sp + kASlabBytes;
+                const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
+                const uint64_t b_desc = ptx::make_kmajor_sw128_desc(b_addr);
 #pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                // +32 bytes per 16-element K step inside the 128 B swizzle span (encoded >> 4)
-                ptx::umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc,
-                              (uint32_t)((kb | k) != 0));
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  // +32 bytes per 16-element K step inside the 128 B swizzle span (encoded >> 4)
+                  if (kCtas == 2)
+                    ptx::umma_f16_2sm(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc, (uint32_t)((kb | k) != 0));
+                  else
+                    ptx::umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc, (uint32_t)((kb | k) != 0));
+                }
+                // ring slot (in both CTAs) reusable when these MMAs retire
+                if (kCtas == 2) ptx::umma_commit_2sm(&ctl->b_empty[stage]); else ptx::umma_commit(&ctl->b_empty[stage]);
+                if (last_use_of_a) {
+                  if (kCtas == 2) ptx::umma_commit_2sm(&ctl->a_empty[kb]); else ptx::umma_commit(&ctl->a_empty[kb]);
+                }
+                // accumulator tile complete (each CTA's epilogue reads its own 128 rows)
+                if (kb == KB - 1) {
+                  if (kCtas == 2) ptx::umma_commit_2sm(&ctl->tmem_full[as]); else ptx::umma_commit(&ctl->tmem_full[as]);
+                }
               }
-              ptx::umma_commit(&ctl->b_empty[stage]);             // ring slot reusable when these MMAs retire
-              if (kResident && pass == 1 && nt == NT - 1) ptx::umma_commit(&ctl->a_empty[kb]);
+              __syncwarp();
+              if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; }
             }
-            ptx::umma_commit(&ctl->tmem_full[as]);                // accumulator tile complete
           }
         }
       }
@@ -234,8 +267,16 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
     const int quarter = warp & 3;                                  // TMEM lanes [32q, 32q+32)
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     uint32_t acc_it = 0;
-    for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x) {
-      const long long row = (long long)tile * kBlockM + quarter * 32 + lane;
+    auto release_acc = [&](uint32_t as) {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kCtas == 2) ptx::mbar_arrive_cluster(&ctl->tmem_empty[as], 0u);   // the leader's MMA warp waits for both CTAs
+        else ptx::mbar_arrive(&ctl->tmem_empty[as]);
+      }
+    };
+    for (int tile = unit; tile < p.n_row_tiles; tile += n_units) {
+      const long long row = (long long)tile * kTileRows + (long long)rank * kBlockM + quarter * 32 + lane;
       const bool row_ok = row < p.n;
       // ---------------- pass 1: running max / first argmax of the raw dot products
       float m = -CUDART_INF_F;
@@ -253,9 +294,7 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
           if (nv >= 32) max_chunk<false>(raw, 32, nt * kBlockN + ch * 32, m, arg);
           else max_chunk<true>(raw, nv, nt * kBlockN + ch * 32, m, arg);
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[as]);
+        release_acc(as);
       }
       // ---------------- pass 2: sum of exp at the predicted class's multiplier
       float cc = 1.0f;
@@ -284,9 +323,7 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
             }
           }
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[as]);
+        release_acc(as);
       }
       // ---------------- per-row results
       if (kMode == 0) {
@@ -309,10 +346,13 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
   }
 
   // ------------------------------------------------------------------ teardown
+  __syncwarp();                                                    // single-lane roles rejoin their warp
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) ptx::cluster_sync_all(); else __syncthreads();   // the peer may still read my SMEM / TMEM until here
   ptx::tc_fence_after();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 1) {
+    if (kCtas == 2) ptx::tmem_dealloc_2sm(tmem_base, kTmemCols); else ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
   if (kMode == 0 && p.table != nullptr) {
     for (int i = threadIdx.x; i <= p.n_thr; i += kThreads) {
       const BinCell cell = ctl->cells[i];
@@ -381,15 +421,36 @@ int make_map(CUtensorMap* map, const void* base, long long rows, int d, int box_
   return CCAL_OK;
 }
 
-template <bool kResident, int kMode>
+template <int kCtas, bool kResident, int kMode>
 static int launch_variant(const CUtensorMap& mi, const CUtensorMap& mt, const ScoreParams& p, const ThrBlock& thr,
                           int grid, size_t smem, cudaStream_t stream) {
-  auto kern = score_fused_kernel<kResident, kMode>;
+  auto kern = score_fused_kernel<kCtas, kResident, kMode>;
   CCAL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kThreads, smem, stream>>>(mi, mt, p, thr);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (kCtas == 2) ? 1 : 0;
+  CCAL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mi, mt, p, thr));
   note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
+}
+
+// CTAs per image tile: 2 (CTA pair, cta_group::2) unless CCAL_SCORE_CTAS=1 is set or the shard is too small
+// to give every pair a tile.
+static int choose_ctas(int64_t n) {
+  const char* e = getenv("CCAL_SCORE_CTAS");
+  if (e && e[0] == '1') return 1;
+  if (e && e[0] == '2') return 2;
+  return n >= (int64_t)kBlockM * 2 * (num_sms() / 2) ? 2 : 1;
 }
 
 static int run_fused(int mode, const void* img, const void* txt, int64_t n, int c, int d, int dtype, ScoreParams p,
@@ -402,37 +463,43 @@ static int run_fused(int mode, const void* img, const void* txt, int64_t n, int 
   CCAL_REQUIRE(dtype == CCAL_BF16 || dtype == CCAL_F16, "fused scoring: operands must be bf16 or fp16");
   CCAL_REQUIRE(img && txt, "fused scoring: NULL feature pointer");
   CCAL_REQUIRE(((uintptr_t)img % 16 == 0) && ((uintptr_t)txt % 16 == 0), "fused scoring: 16-byte alignment required");
-  CCAL_REQUIRE(n <= 2147483647ll - kBlockM, "fused scoring: n must fit int32 row coordinates");
+  CCAL_REQUIRE(n <= 2147483647ll - 2 * kBlockM, "fused scoring: n must fit int32 row coordinates");
 
+  const int ctas = choose_ctas(n);
   CUtensorMap map_img, map_txt;
   rc = make_map(&map_img, img, n, d, kBlockM, dtype);
   if (rc) return rc;
-  rc = make_map(&map_txt, txt, c, d, kBlockN, dtype);
+  rc = make_map(&map_txt, txt, c, d, kBlockN / ctas, dtype);
   if (rc) return rc;
 
   p.n = n; p.c = c; p.d = d;
   p.kblocks = d / kBlockK;
   p.n_col_tiles = (c + kBlockN - 1) / kBlockN;
-  p.n_row_tiles = (int)((n + kBlockM - 1) / kBlockM);
+  const int tile_rows = kBlockM * ctas;
+  p.n_row_tiles = (int)((n + tile_rows - 1) / tile_rows);
   const uint32_t fmt = (dtype == CCAL_BF16) ? 1u : 0u;
-  // tcgen05 instruction descriptor, kind::f16: D=f32, A/B=fmt, both K-major, N=256, M=128
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  // tcgen05 instruction descriptor, kind::f16: D=f32, A/B=fmt, both K-major, N=256, M=128 per CTA
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kBlockN >> 3) << 17) | ((uint32_t)(tile_rows >> 4) << 24);
 
   const int avail = kSmemLimit - kCtlBytes - 1024;          // after control block and alignment slack
+  const int b_bytes = kBTileBytes / ctas;
   const bool resident = (p.kblocks * kASlabBytes + 2 * kBTileBytes) <= avail;
-  int stages = resident ? (avail - p.kblocks * kASlabBytes) / kBTileBytes : avail / (kASlabBytes + kBTileBytes);
+  int stages = resident ? (avail - p.kblocks * kASlabBytes) / b_bytes : avail / (kASlabBytes + b_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
   const size_t smem = kCtlBytes + 1024 +
-                      (resident ? (size_t)p.kblocks * kASlabBytes + (size_t)stages * kBTileBytes
-                                : (size_t)stages * (kASlabBytes + kBTileBytes));
-  const int sms = num_sms();
-  const int grid = p.n_row_tiles < sms ? p.n_row_tiles : sms;
-  if (mode == 0)
-    return resident ? launch_variant<true, 0>(map_img, map_txt, p, thr, grid, smem, stream)
-                    : launch_variant<false, 0>(map_img, map_txt, p, thr, grid, smem, stream);
-  return resident ? launch_variant<true, 1>(map_img, map_txt, p, thr, grid, smem, stream)
-                  : launch_variant<false, 1>(map_img, map_txt, p, thr, grid, smem, stream);
+                      (resident ? (size_t)p.kblocks * kASlabBytes + (size_t)stages * b_bytes
+                                : (size_t)stages * (kASlabBytes + b_bytes));
+  const int units = num_sms() / ctas;
+  const int grid = (p.n_row_tiles < units ? p.n_row_tiles : units) * ctas;
+#define CCAL_LAUNCH(C, R, M) launch_variant<C, R, M>(map_img, map_txt, p, thr, grid, smem, stream)
+  if (ctas == 2) {
+    if (mode == 0) return resident ? CCAL_LAUNCH(2, true, 0) : CCAL_LAUNCH(2, false, 0);
+    return resident ? CCAL_LAUNCH(2, true, 1) : CCAL_LAUNCH(2, false, 1);
+  }
+  if (mode == 0) return resident ? CCAL_LAUNCH(1, true, 0) : CCAL_LAUNCH(1, false, 0);
+  return resident ? CCAL_LAUNCH(1, true, 1) : CCAL_LAUNCH(1, false, 1);
+#undef CCAL_LAUNCH
 }
 
 }  // namespace ccal

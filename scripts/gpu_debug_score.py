@@ -39,7 +39,8 @@ def run(n, c, d, dtype=torch.bfloat16, with_cc=True, seed=0):
         print("   first bad rows", bad, "got", p[bad], "want", pref[bad], "conf", cf[bad], cref[bad], flush=True)
 
 
-for shape in [(128, 256, 64), (128, 256, 512), (1000, 300, 512), (129, 257, 128), (300, 1000, 768), (2048, 49408, 512)]:
+print("CCAL_SCORE_CTAS =", os.environ.get("CCAL_SCORE_CTAS"), flush=True)
+for shape in [(128, 256, 64), (128, 256, 512), (1000, 300, 512), (129, 257, 128), (300, 1000, 768), (2048, 49408, 512), (20000, 1000, 512), (20001, 397, 768)]:
     try:
         run(*shape)
     except Exception as e:  # noqa: BLE001

@@ -204,15 +204,23 @@ def check_scoring(case, cc, pred_ref, conf_ref, gap_ref, ece_ref, counts_ref, dt
     return pred, conf
 
 
+@pytest.fixture(params=["1", "2"], ids=["cta_group1", "cta_pair"])
+def score_ctas(request, monkeypatch):
+    """Run the fused kernel both as single CTAs (tcgen05 cta_group::1) and as CTA pairs (cta_group::2);
+    by default the library picks pairs only for shards of >= 18,944 rows."""
+    monkeypatch.setenv("CCAL_SCORE_CTAS", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("name", ["eurosat", "sun397_l14", "imagenet", "openvocab"])
-def test_fused_scoring_matches_reference(cuda_lib, name, golden, synth_case):
+def test_fused_scoring_matches_reference(cuda_lib, name, golden, synth_case, score_ctas):
     g, case = golden(name), synth_case(name)
     check_scoring(case, g["cc_k5"], g["dac_pred"], g["dac_conf"], g["dac_gap"], float(g["dac_ece10"]), g["dac_counts10"])
     check_scoring(case, None, g["nodac_pred"], g["nodac_conf"], g["nodac_gap"], float(g["nodac_ece10"]), g["nodac_counts10"])
 
 
 @pytest.mark.parametrize("n,c,d", [(1, 1, 64), (127, 255, 64), (129, 257, 128), (1000, 513, 512), (300, 40, 1024), (4096, 3000, 640)])
-def test_fused_scoring_ragged_shapes_fp16_and_bf16(cuda_lib, n, c, d):
+def test_fused_scoring_ragged_shapes_fp16_and_bf16(cuda_lib, n, c, d, score_ctas):
     for dtype, rounding in ((torch.bfloat16, synth.round_to_bf16), (torch.float16, synth.round_to_fp16)):
         case = synth.make_case("ragged", n, c, max(1, c // 2), d, 5, 0.3, seed=n + c, rounding=rounding)
         cc = (0.95 + 0.05 * np.random.default_rng(c).random(c)).astype(np.float32)
@@ -248,7 +256,7 @@ def test_end_to_end_pipeline_and_host_path(cuda_lib, golden, synth_case):
 
 # ----------------------------------------------------------------------------- K5
 @pytest.mark.parametrize("n,c,d,t", [(200, 37, 128, 4.6052), (1000, 500, 512, 4.0), (64, 1000, 768, 5.0)])
-def test_temperature_scaling_loss_and_gradient(cuda_lib, n, c, d, t):
+def test_temperature_scaling_loss_and_gradient(cuda_lib, n, c, d, t, score_ctas):
     case = synth.make_case("ts", n, c, max(1, c // 2), d, 5, 0.3, seed=n)
     loss, grad = tempscaling.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t)
     lref, gref = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t)
