@@ -215,7 +215,6 @@ def main():
     import torch.distributed as dist
     from clip_calibration_b200 import _lib, native, pipeline
     from clip_calibration_b200 import table_math as tm
-    from clip_calibration_b200.trainers.calibration.distanse_aware_calibration import DistanseAwareCalibration
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -299,9 +298,9 @@ def main():
     e2e_table = {}
 
     def e2e_step():
-        dac = DistanseAwareCalibration()
-        dac.fit(host_txt["bz"], host_txt["cz"], host_txt["bt"], host_txt["ct"], K_DAC)       # H2D of the text side
-        scorer = pipeline.CalibratedScorer(host_txt["ct"], dac.class_confidence_device, LOGIT_SCALE, N_BINS)
+        # H2D of the four text matrices + DAC fit (class_confidence stays on the device)
+        scorer = pipeline.CalibratedScorer.from_dac(host_txt["bz"], host_txt["cz"], host_txt["bt"], host_txt["ct"],
+                                                    k=K_DAC, logit_scale=LOGIT_SCALE, n_bins=N_BINS)
         scorer.accumulate_host(host_img, host_labels, chunk_rows=131072)                     # chunked H2D + scoring
         e2e_table["t"] = scorer.reduced_table()                                              # all-reduce + D2H
 
@@ -310,9 +309,8 @@ def main():
     e2e_ms = timed(e2e_step, max(3, args.steps // 2))
     e2e_steps = max(3, args.steps // 2)
     assert tm.total_count(e2e_table["t"]) == N_IMAGES * world
-    h2d = host_img.numel() * 2 + host_labels.numel() * 8 + sum(v.numel() * 4 for v in host_txt.values()) \
-        + host_txt["ct"].numel() * 4
-    d2h = 3 * (N_BINS + 1) * 8 + N_CLASSES * 4
+    h2d = host_img.numel() * 2 + host_labels.numel() * 8 + sum(v.numel() * 4 for v in host_txt.values())
+    d2h = 3 * (N_BINS + 1) * 8
 
     if rank != 0:
         if world > 1:

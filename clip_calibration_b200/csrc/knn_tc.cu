@@ -106,35 +106,37 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
   const int NT = p.n_col_tiles, KB = p.kblocks;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x)
-        for (int nt = 0; nt < NT; ++nt)
-          for (int kb = 0; kb < KB; ++kb, ++it) {
-            const uint32_t stage = it % kTcStages, ph = (it / kTcStages) & 1u;
-            unsigned char* sp = op_ptr + (size_t)stage * kTcStageBytes;
-            ptx::mbar_wait(&ctl->empty[stage], ph ^ 1u);
+    // TMA producer: whole warp loops, one elected lane issues (warp-uniform control flow)
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x)
+      for (int nt = 0; nt < NT; ++nt)
+        for (int kb = 0; kb < KB; ++kb) {
+          unsigned char* sp = op_ptr + (size_t)stage * kTcStageBytes;
+          ptx::mbar_wait(&ctl->empty[stage], phase ^ 1u);
+          if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(&ctl->full[stage], kTcStageBytes);
             ptx::tma_load_2d(sp, &map_qhi, &ctl->full[stage], kb * kTcBlockK, tile * kTcBlockM, ptx::kEvictNormal);
             ptx::tma_load_2d(sp + kTcQBytes, &map_qlo, &ctl->full[stage], kb * kTcBlockK, tile * kTcBlockM, ptx::kEvictNormal);
             ptx::tma_load_2d(sp + 2 * kTcQBytes, &map_rhi, &ctl->full[stage], kb * kTcBlockK, nt * kTcBlockN, ptx::kEvictLast);
             ptx::tma_load_2d(sp + 2 * kTcQBytes + kTcRBytes, &map_rlo, &ctl->full[stage], kb * kTcBlockK, nt * kTcBlockN, ptx::kEvictLast);
           }
-    }
+          __syncwarp();
+          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+        }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t it = 0, acc_it = 0;
-      for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x)
-        for (int nt = 0; nt < NT; ++nt, ++acc_it) {
-          const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-          ptx::mbar_wait(&ctl->tmem_empty[as], aph ^ 1u);
+    // MMA issuer: whole warp waits, one elected lane issues 12 MMAs + commit per 64-feature block
+    uint32_t stage = 0, phase = 0, acc_it = 0;
+    for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x)
+      for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+        const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+        ptx::mbar_wait(&ctl->tmem_empty[as], aph ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kTcBlockN;
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint32_t sp = op_base + stage * kTcStageBytes;
+          ptx::mbar_wait(&ctl->full[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * kTcBlockN;
-          for (int kb = 0; kb < KB; ++kb, ++it) {
-            const uint32_t stage = it % kTcStages, ph = (it / kTcStages) & 1u;
-            const uint32_t sp = op_base + stage * kTcStageBytes;
-            ptx::mbar_wait(&ctl->full[stage], ph);
-            ptx::tc_fence_after();
+          if (ptx::elect_one()) {
             const uint64_t qhi = ptx::make_kmajor_sw128_desc(sp), qlo = ptx::make_kmajor_sw128_desc(sp + kTcQBytes);
             const uint64_t rhi = ptx::make_kmajor_sw128_desc(sp + 2 * kTcQBytes);
             const uint64_t rlo = ptx::make_kmajor_sw128_desc(sp + 2 * kTcQBytes + kTcRBytes);
@@ -146,10 +148,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
               ptx::umma_f16(d_tmem, qlo + o, rhi + o, p.idesc, 1u);
             }
             ptx::umma_commit(&ctl->empty[stage]);
+            if (kb == KB - 1) ptx::umma_commit(&ctl->tmem_full[as]);
           }
-          ptx::umma_commit(&ctl->tmem_full[as]);
+          __syncwarp();
+          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
         }
-    }
+      }
   } else {
     const int quarter = warp & 3;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
@@ -203,6 +207,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
       }
     }
   }
+  __syncwarp();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();

@@ -57,11 +57,12 @@ class CalibratedScorer:
     def from_dac(cls, base_zs, cur_zs, base_tuned, cur_tuned, k: int = 5, **kw):
         """Fit DAC on the four text matrices (this rank, redundantly) and score against the tuned
         test-vocabulary features - what VLBaseLearner.test + build_dac_calibrator set up
-        (base_learner.py:117-119, vl_calibrator.py:155-180)."""
-        from .trainers.calibration.distanse_aware_calibration import DistanseAwareCalibration
+        (base_learner.py:117-119, vl_calibrator.py:155-180).  Host inputs are uploaded once."""
+        from .trainers.calibration.distanse_aware_calibration import DistanseAwareCalibration, _to_cuda_f32
+        cur_tuned_dev = _to_cuda_f32(cur_tuned, "current_text_features_tuned")
         dac = DistanseAwareCalibration()
-        dac.fit(base_zs, cur_zs, base_tuned, cur_tuned, k)
-        obj = cls(cur_tuned, dac.class_confidence_device, **kw)
+        dac.fit(base_zs, cur_zs, base_tuned, cur_tuned_dev, k, sync_host_copy=False)
+        obj = cls(cur_tuned_dev, dac.class_confidence_device, **kw)
         obj.dac = dac
         return obj
 
