@@ -73,3 +73,44 @@ def test_open_vocabulary_full_size_properties(cuda_lib):
     ok = gap > 4e-5
     assert np.array_equal(pred[rows].cpu().numpy()[ok], pref[ok])
     np.testing.assert_allclose(conf[rows].cpu().numpy()[ok], cref[ok], rtol=1e-4)
+
+
+def test_in21k_shard_streaming_variant_properties(cuda_lib):
+    """BASELINE.json configs[4] per-GPU shard: 1.75M images x 21,841 classes x 768-d (the D > 640 streaming
+    variant of the fused kernel, CTA pairs): conservation, determinism, shard additivity, oracle spot check."""
+    n, c, d = 1_750_000, 21841, 768
+    img, txt, labels, cc = device_case(n, c, d, 0.45, 1)
+    cc[:10000] = 1.0
+    thr = tm.uniform_thresholds(15)
+    table = native.new_table(15)
+    pred, conf, _ = native.score_fused(img, txt, cc, 100.0, labels, thr, table)
+    tab = native.table_to_numpy(table)
+    assert tm.total_count(tab) == n and int(tab[:, 1].sum()) == int((pred.long() == labels).sum())
+    assert np.array_equal(tab, native.table_to_numpy(native.bin_stats(conf, pred, labels, thr)))
+    table4 = native.new_table(15)
+    for r in range(4):
+        lo, hi = pipeline.shard_bounds(n, r, 4)
+        p4, c4, _ = native.score_fused(img[lo:hi], txt, cc, 100.0, labels[lo:hi], thr, table4)
+        assert torch.equal(p4, pred[lo:hi]) and torch.equal(c4, conf[lo:hi])
+    assert torch.equal(table, table4)
+    rows = torch.randperm(n, device="cuda")[:2048].sort().values
+    pref, cref, gap = orc.score_chain(img[rows].float().cpu().numpy(), txt.float().cpu().numpy(), cc.cpu().numpy(), 100.0)
+    ok = gap > 4e-5
+    assert np.array_equal(pred[rows].cpu().numpy()[ok], pref[ok])
+    np.testing.assert_allclose(conf[rows].cpu().numpy()[ok], cref[ok], rtol=1e-4)
+
+
+def test_proximity_knn_at_scale_chunked(cuda_lib):
+    """f-1 at production size: 600k test images against 2,000 validation images (query chunking path of the
+    tensor-core kNN, 262,144 rows per chunk) vs the exhaustive scan on a slice and the oracle on a few rows."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    val = torch.nn.functional.normalize(torch.randn(2000, 512, device="cuda", generator=g) + 1.5, dim=-1)
+    qry = torch.nn.functional.normalize(torch.randn(600_000, 512, device="cuda", generator=g) + 1.5, dim=-1)
+    d_tc, i_tc = native.knn_l2(val, qry, 5)
+    for lo in (0, 262144 - 500, 524288 - 500, 600_000 - 1000):
+        sl = slice(lo, lo + 1000)
+        d_ex, i_ex = native.knn_l2(val, qry[sl].contiguous(), 5, exhaustive=True)
+        torch.testing.assert_close(d_tc[sl], d_ex, rtol=2e-6, atol=2e-7)
+        assert (i_tc[sl] != i_ex).float().mean() < 2e-3
+    ref = orc.knn_dists(val.cpu().numpy(), qry[-32:].cpu().numpy(), 5)
+    np.testing.assert_allclose(d_tc[-32:].cpu().numpy(), ref, rtol=3e-6, atol=3e-7)
