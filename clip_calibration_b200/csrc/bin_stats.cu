@@ -7,6 +7,9 @@
 // result does not depend on the grid, the order, or how images are sharded over GPUs.
 #include "ccal_common.cuh"
 
+#include <math.h>
+#include <math_constants.h>
+
 namespace ccal {
 
 constexpr int kBinThreads = 256;
@@ -77,7 +80,9 @@ struct __align__(16) LaneCell {
   unsigned long long sum_fx;
 };
 
-template <typename PredT>
+// kUniform: the thresholds are within half a bin of (i+1)/n_thr (every ECE/MCE table), so the bin is
+// floor(x * n_thr) corrected by at most one step against the exact thresholds: 2 compares instead of n_thr.
+template <typename PredT, bool kUniform>
 __global__ void __launch_bounds__(kBinThreads)
 bin_stats_fast_kernel(const float* __restrict__ conf, const PredT* __restrict__ pred,
                       const long long* __restrict__ gt, long long n,
@@ -92,9 +97,18 @@ bin_stats_fast_kernel(const float* __restrict__ conf, const PredT* __restrict__ 
   __syncthreads();
   LaneCell* mine = cells + (size_t)warp * n_cells * 32 + lane;
 
+  const float fn = (float)n_thr;
   auto add = [&](float x, long long p, long long g) {
     int b = 0;
-    for (int j = 0; j < n_thr; ++j) b += (x >= s_thr[j]) ? 1 : 0;
+    if (kUniform) {
+      // guess g = floor(x * n) clamped to [0, n_thr]; exact answer = #(thr <= x) is g-1, g or g+1
+      int gss = min(max(__float2int_rd(x * fn), 0), n_thr);
+      const float lo = gss > 0 ? s_thr[gss - 1] : -CUDART_INF_F;       // bin gss = [thr[gss-1], thr[gss])
+      const float hi = gss < n_thr ? s_thr[gss] : CUDART_INF_F;
+      b = gss + (x >= hi ? 1 : 0) - (x < lo ? 1 : 0);
+    } else {
+      for (int j = 0; j < n_thr; ++j) b += (x >= s_thr[j]) ? 1 : 0;
+    }
     LaneCell c = mine[b * 32];
     c.count += 1u;
     c.correct += (p == g) ? 1u : 0u;
@@ -233,15 +247,20 @@ extern "C" int ccal_bin_stats(const void* conf, int conf_f64, const void* pred, 
     for (int i = 0; i < CCAL_MAX_THRESHOLDS; ++i) tf.t[i] = i < n_thr ? ceil_to_f32(thresholds_host[i]) : 0.0f;
     const size_t fsmem = sizeof(LaneCell) * kFastWarps * n_cells * 32;
     const int fgrid = grid_for((n + 3) / 4, kBinThreads, 4);
-    if (pred_i64) {
-      CCAL_CUDA_OK(cudaFuncSetAttribute(bin_stats_fast_kernel<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      bin_stats_fast_kernel<long long><<<fgrid, kBinThreads, fsmem, stream>>>((const float*)conf, (const long long*)pred, g, (long long)n, tf, n_thr, table);
-      note_launch();
-    } else {
-      CCAL_CUDA_OK(cudaFuncSetAttribute(bin_stats_fast_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      bin_stats_fast_kernel<int><<<fgrid, kBinThreads, fsmem, stream>>>((const float*)conf, (const int*)pred, g, (long long)n, tf, n_thr, table);
-      note_launch();
-    }
+    bool uniform = n_thr >= 1;
+    for (int i = 0; i < n_thr; ++i)
+      uniform = uniform && fabs(thresholds_host[i] - (double)(i + 1) / n_thr) < 0.25 / n_thr;
+#define CCAL_LAUNCH_FAST(PT, U)                                                                                        \
+  do {                                                                                                                 \
+    CCAL_CUDA_OK(cudaFuncSetAttribute(bin_stats_fast_kernel<PT, U>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                      (int)fsmem));                                                                    \
+    bin_stats_fast_kernel<PT, U><<<fgrid, kBinThreads, fsmem, stream>>>((const float*)conf, (const PT*)pred, g,        \
+                                                                        (long long)n, tf, n_thr, table);               \
+  } while (0)
+    if (pred_i64) { if (uniform) CCAL_LAUNCH_FAST(long long, true); else CCAL_LAUNCH_FAST(long long, false); }
+    else { if (uniform) CCAL_LAUNCH_FAST(int, true); else CCAL_LAUNCH_FAST(int, false); }
+#undef CCAL_LAUNCH_FAST
+    note_launch();
     CCAL_CUDA_OK(cudaGetLastError());
     return CCAL_OK;
   }

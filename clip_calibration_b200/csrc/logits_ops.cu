@@ -168,6 +168,98 @@ logits_rows_kernel(float* __restrict__ logits, const float* __restrict__ class_c
   }
 }
 
+
+// Register-resident variant for 16-byte-aligned rows of up to 2048 classes: one warp per row, the whole
+// row (NV4 float4 per lane) is loaded ONCE with all loads in flight, and every later sweep (max, sum of
+// exp, scaling, write-back) runs from registers.  HBM traffic = the algorithmic bytes.
+template <int NV4, int OP>
+__global__ void __launch_bounds__(256)
+logits_rows_reg_kernel(float* __restrict__ logits, const float* __restrict__ class_conf, long long n, int c,
+                       int* __restrict__ pred_out, float* __restrict__ conf_out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long warp_stride = (long long)gridDim.x * 8;
+  const int c4 = c >> 2;
+  for (long long row = warp0; row < n; row += warp_stride) {
+    float4* x4 = reinterpret_cast<float4*>(logits + row * (long long)c);
+    float4 v[NV4];
+#pragma unroll
+    for (int u = 0; u < NV4; ++u) {
+      const int j = lane + 32 * u;
+      v[u] = (j < c4) ? __ldcs(x4 + j) : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    }
+    MaxIdx m{-CUDART_INF_F, 0x7fffffff};
+#pragma unroll
+    for (int u = 0; u < NV4; ++u) {
+      const int j = 4 * (lane + 32 * u);
+      m = better(m, MaxIdx{v[u].x, j}); m = better(m, MaxIdx{v[u].y, j + 1});
+      m = better(m, MaxIdx{v[u].z, j + 2}); m = better(m, MaxIdx{v[u].w, j + 3});
+    }
+    m = group_argmax<32>(m);
+    const int pred = m.i;
+    const float cc = class_conf ? __ldg(class_conf + pred) : 1.0f;
+    if (OP == kArgmaxOnly) {
+      if (lane == 0) {
+        if (pred_out) pred_out[row] = pred;
+        if (conf_out) conf_out[row] = m.v;
+      }
+      continue;
+    }
+    if (OP == kScaleInPlace) {
+#pragma unroll
+      for (int u = 0; u < NV4; ++u) {
+        const int j = lane + 32 * u;
+        if (j < c4) {
+          float4 o = v[u];
+          o.x = __fmul_rn(o.x, cc); o.y = __fmul_rn(o.y, cc); o.z = __fmul_rn(o.z, cc); o.w = __fmul_rn(o.w, cc);
+          __stcs(x4 + j, o);
+        }
+      }
+      if (lane == 0 && pred_out) pred_out[row] = pred;
+      continue;
+    }
+    const float mcc = __fmul_rn(m.v, cc);
+    auto ex = [&](float t) {
+      const float a = __fsub_rn(__fmul_rn(t, cc), mcc);
+      return OP == kConfidence ? __expf(a) : expf(a);
+    };
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < NV4; ++u) {                 // padded lanes hold -inf -> exp = 0
+      v[u].x = ex(v[u].x); v[u].y = ex(v[u].y); v[u].z = ex(v[u].z); v[u].w = ex(v[u].w);
+      s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+    }
+    s = group_sum<32>(s);
+    if (OP == kSoftmaxInPlace) {
+#pragma unroll
+      for (int u = 0; u < NV4; ++u) {
+        const int j = lane + 32 * u;
+        if (j < c4) {
+          float4 o = v[u];
+          o.x = __fdiv_rn(o.x, s); o.y = __fdiv_rn(o.y, s); o.z = __fdiv_rn(o.z, s); o.w = __fdiv_rn(o.w, s);
+          __stcs(x4 + j, o);
+        }
+      }
+    }
+    if (lane == 0) {
+      if (pred_out) pred_out[row] = pred;
+      if (conf_out) conf_out[row] = 1.0f / s;
+    }
+  }
+}
+
+template <int NV4, int OP>
+static int launch_reg(float* logits, const float* class_conf, int64_t n, int c, int* pred_out, float* conf_out,
+                      cudaStream_t stream) {
+  const long long want = (n + 7) / 8;
+  const long long cap = (long long)num_sms() * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  logits_rows_reg_kernel<NV4, OP><<<grid, 256, 0, stream>>>(logits, class_conf, (long long)n, c, pred_out, conf_out);
+  note_launch();
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}
+
 template <int GROUP, int OP>
 static int launch_group(float* logits, const float* class_conf, int64_t n, int c, int* pred_out, float* conf_out,
                         cudaStream_t stream) {
@@ -186,6 +278,13 @@ static int launch_rows(float* logits, const float* class_conf, int64_t n, int c,
                        cudaStream_t stream) {
   if (c <= 16) return launch_group<1, OP>(logits, class_conf, n, c, pred_out, conf_out, stream);
   if (c <= 128) return launch_group<8, OP>(logits, class_conf, n, c, pred_out, conf_out, stream);
+  if (c <= 2048 && c % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+    const int c4 = c / 4;
+    if (c4 <= 64) return launch_reg<2, OP>(logits, class_conf, n, c, pred_out, conf_out, stream);
+    if (c4 <= 128) return launch_reg<4, OP>(logits, class_conf, n, c, pred_out, conf_out, stream);
+    if (c4 <= 256) return launch_reg<8, OP>(logits, class_conf, n, c, pred_out, conf_out, stream);
+    return launch_reg<16, OP>(logits, class_conf, n, c, pred_out, conf_out, stream);
+  }
   if (c <= 2048) return launch_group<32, OP>(logits, class_conf, n, c, pred_out, conf_out, stream);
   return launch_group<256, OP>(logits, class_conf, n, c, pred_out, conf_out, stream);
 }

@@ -157,7 +157,8 @@ def test_proximity_knn(cuda_lib, golden):
 
 
 # ----------------------------------------------------------------------------- K4
-@pytest.mark.parametrize("n,c", [(1, 1), (77, 10), (300, 397), (129, 2048), (65, 2049), (33, 49408)])
+@pytest.mark.parametrize("n,c", [(1, 1), (77, 10), (300, 397), (129, 2048), (65, 2049), (33, 49408), (1000, 1000),
+                                 (513, 256), (257, 512), (100, 132), (4099, 1028)])
 def test_materialised_logits_dropins(cuda_lib, n, c):
     rng = np.random.default_rng(n * 1000 + c)
     logits = (rng.standard_normal((n, c)) * 8).astype(np.float32)
