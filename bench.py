@@ -158,7 +158,7 @@ def sample_text(rows, fit_classes):
             f"{fit_classes} of {N_CLASSES} classes x {N_BASE} base; both extrapolated linearly to the full job")
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -180,7 +180,7 @@ def run_reference_arm(args):
             "gpu_launches": 0,
             "note": "reference torch/numpy CPU path (oracle port; the Python reference tree is absent on the GPU box), "
                     "ms_per_step extrapolated to the full 1M-image job"}
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
 
 
 def _host_sample(rows):
@@ -197,7 +197,22 @@ def _host_sample(rows):
 # ----------------------------------------------------------------------------------------
 # the CUDA arm
 # ----------------------------------------------------------------------------------------
+class _StdoutToStderr:
+    """Route everything libraries print to fd 1 (e.g. NCCL's version banner) to stderr so that the
+    ONE JSON line is the only thing on stdout; `emit()` writes that line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str) -> None:
+        sys.stdout.flush()
+        os.write(self._real, (line + "\n").encode())
+
+
 def main():
+    out = _StdoutToStderr()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -209,7 +224,7 @@ def main():
         args.warmup = 3
 
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, out)
         return
 
     import torch.distributed as dist
@@ -365,7 +380,7 @@ def main():
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "dac_fit_ms": fit_ms, "check": summary}
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

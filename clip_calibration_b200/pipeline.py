@@ -83,10 +83,13 @@ class CalibratedScorer:
         return pred, conf
 
     def accumulate_host(self, image_features: torch.Tensor, labels: torch.Tensor, chunk_rows: int = 131072,
-                        keep_outputs: bool = False):
+                        keep_outputs: bool = False, ramp: bool = True):
         """End-to-end path for HOST inputs (ideally pinned): the shard is cut into row chunks,
         chunk i+1 is copied host->device on a side stream while chunk i is being scored, and
-        only the bin table (and optionally pred/conf) ever comes back."""
+        only the bin table (and optionally pred/conf) ever comes back.  With `ramp` the first chunks
+        are small (1/8, 1/4, 1/2 of chunk_rows) so scoring starts after a few MB have arrived instead
+        of after a full chunk - the un-overlapped head of the pipeline is what 8 ranks sharing one
+        host's memory bandwidth feel most."""
         if image_features.is_cuda:
             raise ValueError("accumulate_host expects host tensors; use score() for device tensors")
         if image_features.dtype != self.operand_dtype:
@@ -104,8 +107,13 @@ class CalibratedScorer:
         consumed = [torch.cuda.Event() for _ in range(2)]
         preds, confs = [], []
         copy.wait_stream(comp)
-        for i, lo in enumerate(range(0, n, chunk_rows)):
-            hi = min(n, lo + chunk_rows)
+        bounds, lo = [], 0
+        sizes = [chunk_rows // 8, chunk_rows // 4, chunk_rows // 2] if ramp and n > 2 * chunk_rows else []
+        while lo < n:
+            step = max(128, sizes.pop(0)) if sizes else chunk_rows
+            bounds.append((lo, min(n, lo + step)))
+            lo += step
+        for i, (lo, hi) in enumerate(bounds):
             b = i & 1
             with torch.cuda.stream(copy):
                 if i >= 2:
