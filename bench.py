@@ -315,7 +315,8 @@ def main():
     def e2e_step():
         # H2D of the four text matrices + DAC fit (class_confidence stays on the device)
         scorer = pipeline.CalibratedScorer.from_dac(host_txt["bz"], host_txt["cz"], host_txt["bt"], host_txt["ct"],
-                                                    k=K_DAC, logit_scale=LOGIT_SCALE, n_bins=N_BINS)
+                                                    k=K_DAC, logit_scale=LOGIT_SCALE, n_bins=N_BINS,
+                                                    operand_dtype=torch.bfloat16)
         scorer.accumulate_host(host_img, host_labels, chunk_rows=131072)                     # chunked H2D + scoring
         e2e_table["t"] = scorer.reduced_table()                                              # all-reduce + D2H
 

@@ -42,6 +42,15 @@ def _need_cuda(name: str, t: torch.Tensor, dtype=None, ndim=None) -> torch.Tenso
     return t.contiguous()
 
 
+def operand_dtype_for(t: torch.Tensor, requested=None):
+    """16-bit operand dtype of the fused kernels for a feature tensor: fp16 / bf16 inputs are used as
+    they are; wider inputs go to fp16 unless `requested` says otherwise (for L2-normalised features fp16
+    keeps 3 more mantissa bits than bf16 and is what the reference itself runs on the GPU)."""
+    if requested is not None:
+        return requested
+    return t.dtype if t.dtype in (torch.float16, torch.bfloat16) else torch.float16
+
+
 def new_table(n_thr: int, n_thr2: int = 0, device=None) -> torch.Tensor:
     """Zeroed bin table [(n_thr2+1), (n_thr+1), 3] (int64 view of the unsigned counters)."""
     shape = (n_thr + 1, 3) if n_thr2 == 0 else (n_thr2 + 1, n_thr + 1, 3)

@@ -33,9 +33,10 @@ class CalibratedScorer:
     """Text side of the problem, resident on this rank's GPU, plus the running bin table."""
 
     def __init__(self, text_features, class_conf=None, logit_scale: float = 100.0, n_bins: int = 10,
-                 operand_dtype=torch.bfloat16, group=None, device=None):
+                 operand_dtype=None, group=None, device=None):
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.operand_dtype = operand_dtype
+        probe = text_features if isinstance(text_features, torch.Tensor) else torch.from_numpy(np.asarray(text_features)[:1])
+        self.operand_dtype = native.operand_dtype_for(probe, operand_dtype)
         self.txt = self._features(text_features)
         self.class_conf = None
         if class_conf is not None:
@@ -151,7 +152,7 @@ class CalibratedScorer:
 
 
 def score_and_ece(image_features, text_features, labels, class_conf=None, logit_scale: float = 100.0,
-                  n_bins: int = 10, operand_dtype=torch.bfloat16, group=None) -> dict:
+                  n_bins: int = 10, operand_dtype=None, group=None) -> dict:
     """features -> {accuracy, confidence, ece, mce, table, pred, conf} in one fused pass."""
     scorer = CalibratedScorer(text_features, class_conf, logit_scale, n_bins, operand_dtype, group)
     pred, conf = scorer.score(image_features, labels)

@@ -63,7 +63,7 @@ class CustomCLIPCalibration(nn.Module):
     @torch.no_grad()
     def forward_confidence(self, image, class_conf=None):
         _, image_features, text_features = self.logits_encoder(image)
-        dt = image_features.dtype if image_features.dtype in (torch.float16, torch.bfloat16) else torch.bfloat16
+        dt = native.operand_dtype_for(image_features)
         pred, conf, _ = native.score_fused(image_features.to(dt).contiguous(), text_features.to(dt).contiguous(),
                                            class_conf, float(self.scale_learner().item()))
         return pred, conf
@@ -77,12 +77,11 @@ def _operands(image_features, text_features, labels, operand_dtype):
         t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
         return t.detach().cuda()
     img, txt = dev(image_features), dev(text_features)
-    if img.dtype not in (torch.float16, torch.bfloat16):
-        img = img.to(operand_dtype)
+    img = img.to(native.operand_dtype_for(img, operand_dtype))
     return img.contiguous(), txt.to(img.dtype).contiguous(), dev(labels).to(torch.int64).contiguous()
 
 
-def ts_loss_and_grad(image_features, text_features, labels, log_scale: float, operand_dtype=torch.bfloat16):
+def ts_loss_and_grad(image_features, text_features, labels, log_scale: float, operand_dtype=None):
     """(loss, dloss/dlog_scale) as Python floats; one fused two-pass kernel + a fixed-order reduce."""
     img, txt, y = _operands(image_features, text_features, labels, operand_dtype)
     out = native.ts_loss_grad(img, txt, y, float(log_scale)).cpu()
@@ -92,7 +91,7 @@ def ts_loss_and_grad(image_features, text_features, labels, log_scale: float, op
 def fit_logit_scale(image_features, text_features, labels, epochs: int = 20, lr: float = 0.05, batch_size: int = 32,
                     momentum: float = 0.9, weight_decay: float = 5e-4, warmup_epochs: int = 1,
                     warmup_lr: float = 1e-5, init: float = INIT_LOG_SCALE, shuffle_seed: Optional[int] = 0,
-                    operand_dtype=torch.bfloat16) -> float:
+                    operand_dtype=None) -> float:
     """Learn the scalar log-temperature on cached validation features (reference :146-169 runs
     the full CLIP forward for every batch of every epoch to fit this one parameter)."""
     img, txt, y = _operands(image_features, text_features, labels, operand_dtype)

@@ -234,7 +234,7 @@ def test_fused_scoring_ragged_shapes_fp16_and_bf16(cuda_lib, n, c, d, score_ctas
 def test_end_to_end_pipeline_and_host_path(cuda_lib, golden, synth_case):
     g, case = golden("imagenet"), synth_case("imagenet")
     scorer = pipeline.CalibratedScorer.from_dac(case.base_zs, case.txt_zs, case.base_tuned, case.txt_tuned, k=5,
-                                                logit_scale=case.logit_scale, n_bins=10)
+                                                logit_scale=case.logit_scale, n_bins=10, operand_dtype=torch.bfloat16)
     pred, conf = scorer.score(case.img, case.labels)
     s = scorer.summary()
     assert s["n"] == len(case.labels)
@@ -275,6 +275,34 @@ def test_fit_logit_scale_reduces_loss_and_checkpoint_roundtrip(cuda_lib, tmp_pat
     assert abs(tempscaling.load_logit_scale(str(tmp_path), 5) - t) < 1e-6
     learner = tempscaling.ScaleLearner(None, torch.float32)
     assert abs(float(learner()) - np.exp(4.6052)) < 1e-3 and list(learner.state_dict()) == ["logit_scale"]
+
+
+def test_empty_inputs(cuda_lib):
+    e_img = torch.zeros((0, 64), dtype=torch.bfloat16, device="cuda")
+    txt = torch.zeros((5, 64), dtype=torch.bfloat16, device="cuda")
+    pred, conf, _ = native.score_fused(e_img, txt)
+    assert pred.numel() == 0 and conf.numel() == 0
+    tab = native.bin_stats(torch.zeros(0, device="cuda"), torch.zeros(0, dtype=torch.int32, device="cuda"),
+                           torch.zeros(0, dtype=torch.int64, device="cuda"), tm.uniform_thresholds(10))
+    assert int(tab.sum()) == 0
+    d, i = native.knn_l2(torch.randn(7, 64, device="cuda"), torch.zeros((0, 64), device="cuda"), 3)
+    assert d.shape == (0, 3) and i.shape == (0, 3)
+    p, c = native.logits_confidence(torch.zeros((0, 9), device="cuda"))
+    assert p.numel() == 0 and c.numel() == 0
+
+
+def test_wide_inputs_default_to_fp16_operands(cuda_lib):
+    """fp32 features are not rounded to bf16 behind the user's back: the default operand dtype for wide
+    inputs is fp16 (what the reference runs on the GPU), 8x finer than bf16 for unit-norm features."""
+    case = synth.make_case("fp32", 2000, 300, 150, 512, 5, 0.3, seed=4, rounding=lambda x: np.asarray(x, np.float32))
+    dac = DistanseAwareCalibration()
+    dac.class_confidence = np.ones(300)
+    pred, conf = dac.predict_from_features(case.img, case.txt_tuned, 100.0)
+    pref, cref, gap = orc.score_chain(case.img, case.txt_tuned, None, 100.0)
+    ok = gap > 0.05                                        # fp16 rounding moves logits by ~1e-2
+    assert np.array_equal(pred[ok], pref[ok])
+    np.testing.assert_allclose(conf[ok], cref[ok], rtol=3e-2)
+    assert np.median(np.abs(conf[ok] - cref[ok]) / cref[ok]) < 2e-3
 
 
 # ----------------------------------------------------------------------------- errors
