@@ -67,5 +67,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+C_DEMO_SRC = os.path.join(os.path.dirname(HERE), "examples", "c_abi_smoke.c")
+C_DEMO_BIN = os.path.join(HERE, "c_abi_smoke")
+
+
+def build_c_demo() -> str:
+    """Plain-C client of the ABI (no Python / torch): examples/c_abi_smoke.c -> clip_calibration_b200/c_abi_smoke."""
+    build()
+    if os.path.exists(C_DEMO_BIN) and os.path.getmtime(C_DEMO_BIN) >= max(os.path.getmtime(C_DEMO_SRC), os.path.getmtime(LIB)):
+        return C_DEMO_BIN
+    cmd = [_nvcc(), "-O2", "-x", "cu", "-gencode", "arch=compute_100a,code=sm_100a", "-o", C_DEMO_BIN, C_DEMO_SRC,
+           "-I", os.path.join(os.path.dirname(HERE), "include"), "-L", HERE, "-lccal",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return C_DEMO_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_c_demo())

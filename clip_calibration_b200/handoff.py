@@ -14,8 +14,6 @@ from __future__ import annotations
 
 import os
 import os.path as osp
-from typing import Optional
-
 import numpy as np
 import torch
 

@@ -6,14 +6,13 @@ Nothing here computes on the CPU or through ATen kernels, and nothing falls back
 """
 from __future__ import annotations
 
-import ctypes
 from typing import Optional, Sequence
 
 import numpy as np
 import torch
 
 from . import _lib
-from ._lib import CCAL_BF16, CCAL_F16, FX_SHIFT, MAX_K, MAX_THRESHOLDS
+from ._lib import CCAL_BF16, CCAL_F16
 
 _DTYPES = {torch.bfloat16: CCAL_BF16, torch.float16: CCAL_F16}
 def launch_count() -> int:

@@ -13,8 +13,6 @@ point, so the 1-GPU and the N-GPU results are bit-identical.
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import numpy as np
 import torch
 

@@ -12,8 +12,6 @@ calibration_summary, and the `group=` argument that all-reduces tables across ra
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import numpy as np
 import torch
 

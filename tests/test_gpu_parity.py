@@ -6,6 +6,8 @@ Tolerances (BASELINE.json north_star): predicted labels and kNN indices bit-exac
 flip those); confidences within 1e-4 relative; ECE within 1e-5 absolute; bin counts exact
 except samples within 1e-6 of a bin edge.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -275,6 +277,17 @@ def test_fit_logit_scale_reduces_loss_and_checkpoint_roundtrip(cuda_lib, tmp_pat
     assert abs(tempscaling.load_logit_scale(str(tmp_path), 5) - t) < 1e-6
     learner = tempscaling.ScaleLearner(None, torch.float32)
     assert abs(float(learner()) - np.exp(4.6052)) < 1e-3 and list(learner.state_dict()) == ["logit_scale"]
+
+
+def test_c_abi_from_plain_c(cuda_lib):
+    """examples/c_abi_smoke.c: the library driven from C (cudaMalloc'ed buffers, its own stream, no torch)."""
+    import subprocess
+    from clip_calibration_b200 import build as _build
+    exe = _build.C_DEMO_BIN
+    assert os.path.exists(exe), "run python -m clip_calibration_b200.build (builds the C demo too)"
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "C ABI smoke: OK" in res.stdout
 
 
 def test_empty_inputs(cuda_lib):
