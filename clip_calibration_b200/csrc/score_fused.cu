@@ -19,6 +19,7 @@
 #include "ccal_common.cuh"
 #include "sm100_ptx.cuh"
 
+#include <cuda_fp16.h>
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -68,6 +69,7 @@ struct ScoreParams {
   int n_thr;
   unsigned long long* table;
   float* row_ws;                       // kMode 1: [2*n] per-row loss / gradient terms
+  const int* split_exps;               // kSplit: {e_img, e_txt}: operands were pre-scaled by 2^e before the fp16 split
 };
 
 
@@ -120,10 +122,15 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&raw)[32], int nv, flo
 //            rows resident and loads only HALF of every text tile (128 classes); the pair's leader issues
 //            256x256x16 MMAs that read both halves.  Halves the L2->SMEM text traffic and the SMEM->tensor
 //            B traffic per flop - on a power-capped B200 that is what buys throughput.
-template <int kCtas, bool kResident, int kMode>
+// kSplit (fp32 features, streaming only): every operand arrives as an fp16 pair x*2^e = hi + lo and each K step
+//            issues hi.hi + hi.lo + lo.hi (the dropped lo.lo term is < 2^-22 |a||b|): fp32-grade logits from
+//            16-bit tensor-core operands at 3x the MMA work.
+template <int kCtas, bool kResident, int kMode, bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1)
 score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_constant__ CUtensorMap map_txt,
+                   const __grid_constant__ CUtensorMap map_img_lo, const __grid_constant__ CUtensorMap map_txt_lo,
                    const __grid_constant__ ScoreParams p, const __grid_constant__ ThrBlock thr) {
+  static_assert(!(kSplit && kResident), "the split-precision variant streams both operands");
   extern __shared__ unsigned char smem_dyn[];
   ScoreCtl* ctl = reinterpret_cast<ScoreCtl*>(smem_dyn);
   // operand area starts at the next 1024-byte boundary (128B-swizzle atoms are 1024 B)
@@ -134,7 +141,8 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
   constexpr int kBRows = kBlockN / kCtas;                // classes this CTA loads per text tile
   constexpr int kTileRows = kBlockM * kCtas;             // image rows per (pair) tile
   // resident: [A slab 0..kblocks) then ring of B tiles; streaming: ring of {A slab, B tile}
-  const uint32_t stage_bytes = kResident ? kBBytes : (kASlabBytes + kBBytes);
+  constexpr int kParts = kSplit ? 2 : 1;                 // hi (+ lo) copies of each operand per stage
+  const uint32_t stage_bytes = kResident ? kBBytes : kParts * (kASlabBytes + kBBytes);
   unsigned char* ring_ptr = op_ptr + (kResident ? p.kblocks * kASlabBytes : 0);
 
   const int warp = threadIdx.x >> 5;
@@ -195,13 +203,23 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
                 if (kCtas == 2) ptx::tma_load_2d_2sm(sp, &map_txt, &ctl->b_full[stage], kb * kBlockK, col0, ptx::kEvictLast);
                 else ptx::tma_load_2d(sp, &map_txt, &ctl->b_full[stage], kb * kBlockK, col0, ptx::kEvictLast);
               } else {
-                if (leader) ptx::mbar_arrive_expect_tx(&ctl->b_full[stage], (kASlabBytes + kBBytes) * kCtas);
+                // stage layout: [A hi][A lo?][B hi][B lo?]
+                unsigned char* sb = sp + kParts * kASlabBytes;
+                if (leader) ptx::mbar_arrive_expect_tx(&ctl->b_full[stage], kParts * (kASlabBytes + kBBytes) * kCtas);
                 if (kCtas == 2) {
                   ptx::tma_load_2d_2sm(sp, &map_img, &ctl->b_full[stage], kb * kBlockK, row0, ptx::kEvictNormal);
-                  ptx::tma_load_2d_2sm(sp + kASlabBytes, &map_txt, &ctl->b_full[stage], kb * kBlockK, col0, ptx::kEvictLast);
+                  ptx::tma_load_2d_2sm(sb, &map_txt, &ctl->b_full[stage], kb * kBlockK, col0, ptx::kEvictLast);
+                  if (kSplit) {
+                    ptx::tma_load_2d_2sm(sp + kASlabBytes, &map_img_lo, &ctl->b_full[stage], kb * kBlockK, row0, ptx::kEvictNormal);
+                    ptx::tma_load_2d_2sm(sb + kBBytes, &map_txt_lo, &ctl->b_full[stage], kb * kBlockK, col0, ptx::kEvictLast);
+                  }
                 } else {
                   ptx::tma_load_2d(sp, &map_img, &ctl->b_full[stage], kb * kBlockK, row0, ptx::kEvictNormal);
-                  ptx::tma_load_2d(sp + kASlabBytes, &map_txt, &ctl->b_full[stage], kb * kBlockK, col0, ptx::kEvictLast);
+                  ptx::tma_load_2d(sb, &map_txt, &ctl->b_full[stage], kb * kBlockK, col0, ptx::kEvictLast);
+                  if (kSplit) {
+                    ptx::tma_load_2d(sp + kASlabBytes, &map_img_lo, &ctl->b_full[stage], kb * kBlockK, row0, ptx::kEvictNormal);
+                    ptx::tma_load_2d(sb + kBBytes, &map_txt_lo, &ctl->b_full[stage], kb * kBlockK, col0, ptx::kEvictLast);
+                  }
                 }
               }
             }
@@ -234,16 +252,20 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
               ptx::tc_fence_after();
               if (ptx::elect_one()) {
                 const uint32_t a_addr = kResident ? op_base + (uint32_t)kb * kASlabBytes : sp;
-                const uint32_t b_addr = kResident ? sp : sp + kASlabBytes;
+                const uint32_t b_addr = kResident ? sp : sp + kParts * kASlabBytes;
                 const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_addr);
                 const uint64_t b_desc = ptx::make_kmajor_sw128_desc(b_addr);
+                const uint64_t a_lo = kSplit ? ptx::make_kmajor_sw128_desc(a_addr + kASlabBytes) : 0;
+                const uint64_t b_lo = kSplit ? ptx::make_kmajor_sw128_desc(b_addr + kBBytes) : 0;
+                auto mma = [&](uint64_t ad, uint64_t bd, uint32_t acc) {
+                  if (kCtas == 2) ptx::umma_f16_2sm(d_tmem, ad, bd, p.idesc, acc); else ptx::umma_f16(d_tmem, ad, bd, p.idesc, acc);
+                };
 #pragma unroll
                 for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                   // +32 bytes per 16-element K step inside the 128 B swizzle span (encoded >> 4)
-                  if (kCtas == 2)
-                    ptx::umma_f16_2sm(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc, (uint32_t)((kb | k) != 0));
-                  else
-                    ptx::umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), p.idesc, (uint32_t)((kb | k) != 0));
+                  const uint64_t o = (uint64_t)(k * 2);
+                  mma(a_desc + o, b_desc + o, (uint32_t)((kb | k) != 0));
+                  if (kSplit) { mma(a_desc + o, b_lo + o, 1u); mma(a_lo + o, b_desc + o, 1u); }
                 }
                 // ring slot (in both CTAs) reusable when these MMAs retire
                 if (kCtas == 2) ptx::umma_commit_2sm(&ctl->b_empty[stage]); else ptx::umma_commit(&ctl->b_empty[stage]);
@@ -267,6 +289,8 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
     const int quarter = warp & 3;                                  // TMEM lanes [32q, 32q+32)
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     uint32_t acc_it = 0;
+    // split operands were pre-scaled by powers of two: fold 2^-(e_img + e_txt) into the logit scale (exact)
+    const float scale = kSplit ? p.scale * exp2f(-(float)(p.split_exps[0] + p.split_exps[1])) : p.scale;
     auto release_acc = [&](uint32_t as) {
       ptx::tc_fence_before();
       __syncwarp();
@@ -299,7 +323,7 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
       // ---------------- pass 2: sum of exp at the predicted class's multiplier
       float cc = 1.0f;
       if (kMode == 0 && p.class_conf != nullptr) cc = __ldg(p.class_conf + arg);
-      const float a2 = cc * p.scale * kLog2e;
+      const float a2 = cc * scale * kLog2e;
       const float b2 = m * a2;
       float sum = 0.f, wsum = 0.f, zy = 0.f;
       const int label = (kMode == 1 && row_ok) ? (int)p.labels[row] : -1;
@@ -331,7 +355,7 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
         if (row_ok) {
           if (p.pred_out) p.pred_out[row] = arg;
           if (p.conf_out) p.conf_out[row] = conf;
-          if (p.rowmax_out) p.rowmax_out[row] = m * p.scale;
+          if (p.rowmax_out) p.rowmax_out[row] = m * scale;
         }
         if (p.table != nullptr) {
           const bool correct = row_ok && ((long long)arg == p.labels[row]);
@@ -339,8 +363,8 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
         }
       } else if (row_ok) {
         // loss_i = logsumexp_j(s z_j) - s z_y ;  d loss_i / dt = s (sum_j p_j z_j - z_y), s = exp(t)
-        p.row_ws[row] = logf(sum) + p.scale * (m - zy);
-        p.row_ws[p.n + row] = p.scale * (wsum / sum - zy);
+        p.row_ws[row] = logf(sum) + scale * (m - zy);
+        p.row_ws[p.n + row] = scale * (wsum / sum - zy);
       }
     }
   }
@@ -421,10 +445,10 @@ int make_map(CUtensorMap* map, const void* base, long long rows, int d, int box_
   return CCAL_OK;
 }
 
-template <int kCtas, bool kResident, int kMode>
-static int launch_variant(const CUtensorMap& mi, const CUtensorMap& mt, const ScoreParams& p, const ThrBlock& thr,
-                          int grid, size_t smem, cudaStream_t stream) {
-  auto kern = score_fused_kernel<kCtas, kResident, kMode>;
+template <int kCtas, bool kResident, int kMode, bool kSplit>
+static int launch_variant(const CUtensorMap& mi, const CUtensorMap& mt, const CUtensorMap& mi_lo, const CUtensorMap& mt_lo,
+                          const ScoreParams& p, const ThrBlock& thr, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = score_fused_kernel<kCtas, kResident, kMode, kSplit>;
   CCAL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -438,7 +462,7 @@ static int launch_variant(const CUtensorMap& mi, const CUtensorMap& mt, const Sc
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (kCtas == 2) ? 1 : 0;
-  CCAL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mi, mt, p, thr));
+  CCAL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mi, mt, mi_lo, mt_lo, p, thr));
   note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
@@ -453,24 +477,17 @@ static int choose_ctas(int64_t n) {
   return n >= (int64_t)kBlockM * 2 * (num_sms() / 2) ? 2 : 1;
 }
 
-static int run_fused(int mode, const void* img, const void* txt, int64_t n, int c, int d, int dtype, ScoreParams p,
-                     const ThrBlock& thr, cudaStream_t stream) {
-  int rc = ccal_check_device();
-  if (rc) return rc;
-  CCAL_REQUIRE(n >= 1 && c >= 1, "fused scoring: bad shape n=%lld c=%d", (long long)n, c);
-  CCAL_REQUIRE(d >= 64 && d % 64 == 0 && d <= 64 * kMaxKBlocks,
-               "fused scoring: feature width must be a multiple of 64 in [64, %d] (got %d)", 64 * kMaxKBlocks, d);
-  CCAL_REQUIRE(dtype == CCAL_BF16 || dtype == CCAL_F16, "fused scoring: operands must be bf16 or fp16");
-  CCAL_REQUIRE(img && txt, "fused scoring: NULL feature pointer");
-  CCAL_REQUIRE(((uintptr_t)img % 16 == 0) && ((uintptr_t)txt % 16 == 0), "fused scoring: 16-byte alignment required");
-  CCAL_REQUIRE(n <= 2147483647ll - 2 * kBlockM, "fused scoring: n must fit int32 row coordinates");
-
+// One launch over 16-bit operands.  `img_lo` / `txt_lo` != NULL selects the split-precision variant.
+static int launch_fused(int mode, const void* img, const void* txt, const void* img_lo, const void* txt_lo, int64_t n,
+                        int c, int d, int dtype, ScoreParams p, const ThrBlock& thr, cudaStream_t stream) {
+  const bool split = img_lo != nullptr;
   const int ctas = choose_ctas(n);
-  CUtensorMap map_img, map_txt;
-  rc = make_map(&map_img, img, n, d, kBlockM, dtype);
-  if (rc) return rc;
-  rc = make_map(&map_txt, txt, c, d, kBlockN / ctas, dtype);
-  if (rc) return rc;
+  CUtensorMap map_img, map_txt, map_img_lo, map_txt_lo;
+  int rc;
+  if ((rc = make_map(&map_img, img, n, d, kBlockM, dtype))) return rc;
+  if ((rc = make_map(&map_txt, txt, c, d, kBlockN / ctas, dtype))) return rc;
+  if ((rc = make_map(&map_img_lo, split ? img_lo : img, n, d, kBlockM, dtype))) return rc;
+  if ((rc = make_map(&map_txt_lo, split ? txt_lo : txt, c, d, kBlockN / ctas, dtype))) return rc;
 
   p.n = n; p.c = c; p.d = d;
   p.kblocks = d / kBlockK;
@@ -483,23 +500,128 @@ static int run_fused(int mode, const void* img, const void* txt, int64_t n, int 
 
   const int avail = kSmemLimit - kCtlBytes - 1024;          // after control block and alignment slack
   const int b_bytes = kBTileBytes / ctas;
-  const bool resident = (p.kblocks * kASlabBytes + 2 * kBTileBytes) <= avail;
-  int stages = resident ? (avail - p.kblocks * kASlabBytes) / b_bytes : avail / (kASlabBytes + b_bytes);
+  const int parts = split ? 2 : 1;
+  const bool resident = !split && (p.kblocks * kASlabBytes + 2 * kBTileBytes) <= avail;
+  int stages = resident ? (avail - p.kblocks * kASlabBytes) / b_bytes : avail / (parts * (kASlabBytes + b_bytes));
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
   const size_t smem = kCtlBytes + 1024 +
                       (resident ? (size_t)p.kblocks * kASlabBytes + (size_t)stages * b_bytes
-                                : (size_t)stages * (kASlabBytes + b_bytes));
+                                : (size_t)stages * parts * (kASlabBytes + b_bytes));
   const int units = num_sms() / ctas;
   const int grid = (p.n_row_tiles < units ? p.n_row_tiles : units) * ctas;
-#define CCAL_LAUNCH(C, R, M) launch_variant<C, R, M>(map_img, map_txt, p, thr, grid, smem, stream)
-  if (ctas == 2) {
-    if (mode == 0) return resident ? CCAL_LAUNCH(2, true, 0) : CCAL_LAUNCH(2, false, 0);
-    return resident ? CCAL_LAUNCH(2, true, 1) : CCAL_LAUNCH(2, false, 1);
+#define CCAL_LAUNCH(C, R, M, S) \
+  launch_variant<C, R, M, S>(map_img, map_txt, map_img_lo, map_txt_lo, p, thr, grid, smem, stream)
+  if (split) {
+    if (ctas == 2) return mode == 0 ? CCAL_LAUNCH(2, false, 0, true) : CCAL_LAUNCH(2, false, 1, true);
+    return mode == 0 ? CCAL_LAUNCH(1, false, 0, true) : CCAL_LAUNCH(1, false, 1, true);
   }
-  if (mode == 0) return resident ? CCAL_LAUNCH(1, true, 0) : CCAL_LAUNCH(1, false, 0);
-  return resident ? CCAL_LAUNCH(1, true, 1) : CCAL_LAUNCH(1, false, 1);
+  if (ctas == 2) {
+    if (mode == 0) return resident ? CCAL_LAUNCH(2, true, 0, false) : CCAL_LAUNCH(2, false, 0, false);
+    return resident ? CCAL_LAUNCH(2, true, 1, false) : CCAL_LAUNCH(2, false, 1, false);
+  }
+  if (mode == 0) return resident ? CCAL_LAUNCH(1, true, 0, false) : CCAL_LAUNCH(1, false, 0, false);
+  return resident ? CCAL_LAUNCH(1, true, 1, false) : CCAL_LAUNCH(1, false, 1, false);
 #undef CCAL_LAUNCH
+}
+
+// ---- fp32 features: x * 2^e = hi + lo in fp16, e chosen per matrix so that max|x| * 2^e is in [2^9, 2^10)
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float* __restrict__ x, long long n_elems, unsigned int* __restrict__ max_bits) {
+  float m = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(max_bits, __float_as_uint(m));   // non-negative floats order like uints
+}
+
+__global__ void choose_exponents_kernel(const unsigned int* __restrict__ max_bits, int* __restrict__ exps) {
+  if (threadIdx.x < 2) {
+    const float m = __uint_as_float(max_bits[threadIdx.x]);
+    int e = 0;
+    if (m > 0.f && isfinite(m)) e = 9 - ilogbf(m);
+    exps[threadIdx.x] = max(-100, min(100, e));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ x, long long n_elems, const int* __restrict__ exp_ptr, __half* __restrict__ hi,
+                 __half* __restrict__ lo) {
+  const float s = exp2f((float)*exp_ptr);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems / 4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float f[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+    __half h[4], l[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { h[u] = __float2half_rn(f[u]); l[u] = __float2half_rn(f[u] - __half2float(h[u])); }
+    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+    reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+  }
+}
+
+static int grid_for_elems(long long n, int per_thread) {
+  long long want = (n / per_thread + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+static int run_fused(int mode, const void* img, const void* txt, int64_t n, int c, int d, int dtype, ScoreParams p,
+                     const ThrBlock& thr, cudaStream_t stream) {
+  int rc = ccal_check_device();
+  if (rc) return rc;
+  CCAL_REQUIRE(n >= 1 && c >= 1, "fused scoring: bad shape n=%lld c=%d", (long long)n, c);
+  CCAL_REQUIRE(d >= 64 && d % 64 == 0 && d <= 64 * kMaxKBlocks,
+               "fused scoring: feature width must be a multiple of 64 in [64, %d] (got %d)", 64 * kMaxKBlocks, d);
+  CCAL_REQUIRE(dtype == CCAL_BF16 || dtype == CCAL_F16 || dtype == CCAL_F32, "fused scoring: unknown operand dtype %d", dtype);
+  CCAL_REQUIRE(img && txt, "fused scoring: NULL feature pointer");
+  CCAL_REQUIRE(((uintptr_t)img % 16 == 0) && ((uintptr_t)txt % 16 == 0), "fused scoring: 16-byte alignment required");
+  CCAL_REQUIRE(n <= 2147483647ll - 2 * kBlockM, "fused scoring: n must fit int32 row coordinates");
+  if (dtype != CCAL_F32) return launch_fused(mode, img, txt, nullptr, nullptr, n, c, d, dtype, p, thr, stream);
+
+  // ---- fp32 features: split into fp16 pairs (transient stream-ordered workspace), score chunk by chunk
+  const int64_t chunk = n < 262144 ? n : 262144;
+  CCAL_REQUIRE(mode == 0 || n <= chunk, "ccal_ts_loss_grad with fp32 operands supports up to %lld rows per call", (long long)chunk);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_thi = take((size_t)c * d * 2), o_tlo = take((size_t)c * d * 2);
+  const size_t o_ihi = take((size_t)chunk * d * 2), o_ilo = take((size_t)chunk * d * 2);
+  const size_t o_max = take(8), o_exp = take(8);
+  unsigned char* ws = nullptr;
+  CCAL_CUDA_OK(cudaMallocAsync((void**)&ws, off, stream));
+  unsigned int* maxbits = (unsigned int*)(ws + o_max);
+  int* exps = (int*)(ws + o_exp);
+  const float* fimg = (const float*)img;
+  const float* ftxt = (const float*)txt;
+  CCAL_CUDA_OK(cudaMemsetAsync(maxbits, 0, 8, stream));
+  absmax_kernel<<<grid_for_elems((long long)n * d, 4), 256, 0, stream>>>(fimg, (long long)n * d, maxbits);
+  note_launch();
+  absmax_kernel<<<grid_for_elems((long long)c * d, 4), 256, 0, stream>>>(ftxt, (long long)c * d, maxbits + 1);
+  note_launch();
+  choose_exponents_kernel<<<1, 32, 0, stream>>>(maxbits, exps);
+  note_launch();
+  split_f16_kernel<<<grid_for_elems((long long)c * d, 4), 256, 0, stream>>>(ftxt, (long long)c * d, exps + 1, (__half*)(ws + o_thi),
+                                                                           (__half*)(ws + o_tlo));
+  note_launch();
+  p.split_exps = exps;
+  rc = CCAL_OK;
+  for (int64_t q0 = 0; q0 < n && rc == CCAL_OK; q0 += chunk) {
+    const int64_t m = (n - q0) < chunk ? (n - q0) : chunk;
+    split_f16_kernel<<<grid_for_elems((long long)m * d, 4), 256, 0, stream>>>(fimg + q0 * d, (long long)m * d, exps, (__half*)(ws + o_ihi),
+                                                                             (__half*)(ws + o_ilo));
+    note_launch();
+    ScoreParams pc = p;
+    if (pc.pred_out) pc.pred_out += q0;
+    if (pc.conf_out) pc.conf_out += q0;
+    if (pc.rowmax_out) pc.rowmax_out += q0;
+    if (pc.labels) pc.labels += q0;
+    rc = launch_fused(mode, ws + o_ihi, ws + o_thi, ws + o_ilo, ws + o_tlo, m, c, d, CCAL_F16, pc, thr, stream);
+  }
+  cudaFreeAsync(ws, stream);
+  CCAL_CUDA_OK(cudaGetLastError());
+  return rc;
 }
 
 }  // namespace ccal

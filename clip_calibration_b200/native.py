@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from ._lib import CCAL_BF16, CCAL_F16
 
-_DTYPES = {torch.bfloat16: CCAL_BF16, torch.float16: CCAL_F16}
+_DTYPES = {torch.bfloat16: CCAL_BF16, torch.float16: CCAL_F16, torch.float32: 0}
 def launch_count() -> int:
     """Kernels launched by libccal.so in this process (counted inside the library at each launch site)."""
     return int(_lib.load().ccal_launch_count())
@@ -42,12 +42,15 @@ def _need_cuda(name: str, t: torch.Tensor, dtype=None, ndim=None) -> torch.Tenso
 
 
 def operand_dtype_for(t: torch.Tensor, requested=None):
-    """16-bit operand dtype of the fused kernels for a feature tensor: fp16 / bf16 inputs are used as
-    they are; wider inputs go to fp16 unless `requested` says otherwise (for L2-normalised features fp16
-    keeps 3 more mantissa bits than bf16 and is what the reference itself runs on the GPU)."""
+    """Operand dtype of the fused kernels for a feature tensor.  fp16 / bf16 features go to the tensor
+    cores as they are (exact products, fp32 accumulation).  fp32 (or wider) features default to
+    torch.float32 = the split-precision mode: each operand becomes an fp16 pair hi + lo and every K step
+    issues hi.hi + hi.lo + lo.hi, which reproduces the reference's fp32 logits to ~1e-4 absolute at s=100
+    (confidences to <1e-4 relative) at 3x the tensor work.  Pass torch.float16 / torch.bfloat16 to round
+    the features instead (3.7x faster; confidences then move by ~3e-3 / ~3e-2 relative)."""
     if requested is not None:
         return requested
-    return t.dtype if t.dtype in (torch.float16, torch.bfloat16) else torch.float16
+    return t.dtype if t.dtype in (torch.float16, torch.bfloat16) else torch.float32
 
 
 def new_table(n_thr: int, n_thr2: int = 0, device=None) -> torch.Tensor:
@@ -71,7 +74,7 @@ def score_fused(img: torch.Tensor, txt: torch.Tensor, class_conf: Optional[torch
     softmax(cc[pred] * logit_scale * img @ txt.T) without materialising logits.
     Returns (pred int32 [N] | None, conf float32 [N] | None, rowmax float32 [N] | None)."""
     lib = _lib.load()
-    img = _need_cuda("img", img, (torch.bfloat16, torch.float16), 2)
+    img = _need_cuda("img", img, (torch.bfloat16, torch.float16, torch.float32), 2)
     txt = _need_cuda("txt", txt, img.dtype, 2)
     if img.shape[1] != txt.shape[1]:
         raise ValueError(f"feature widths differ: img {tuple(img.shape)} vs txt {tuple(txt.shape)}")
@@ -113,7 +116,7 @@ def ts_loss_grad(img: torch.Tensor, txt: torch.Tensor, labels: torch.Tensor, log
     """(loss, d loss / d log_scale) of cross_entropy(exp(log_scale) * img @ txt.T, labels) as a
     float64 CUDA tensor of 2 elements (no host sync)."""
     lib = _lib.load()
-    img = _need_cuda("img", img, (torch.bfloat16, torch.float16), 2)
+    img = _need_cuda("img", img, (torch.bfloat16, torch.float16, torch.float32), 2)
     txt = _need_cuda("txt", txt, img.dtype, 2)
     labels = _need_cuda("labels", labels, torch.int64, 1)
     n, d = img.shape

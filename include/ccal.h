@@ -71,8 +71,11 @@ CCAL_API int ccal_check_device(void);
  *   argmax + confidence gather       (evaluators/vl_evaluator.py:68, :83)
  *   and, when `table` is given, the binning of tools/metrics.py:104-127.
  *
- * img [n,d], txt [c,d] in `dtype` (CCAL_BF16 or CCAL_F16), d a multiple of 64 and <= 1024,
- * base pointers 16-byte aligned.  class_conf [c] float or NULL (= all ones, plain softmax).
+ * img [n,d], txt [c,d] in `dtype`, d a multiple of 64 and <= 1024, base pointers 16-byte aligned.
+ * CCAL_BF16 / CCAL_F16: operands go to the tensor cores as they are (products exact, fp32 accumulate).
+ * CCAL_F32: every operand is split on the fly into an fp16 pair (x*2^e = hi + lo) and each K step issues
+ * hi.hi + hi.lo + lo.hi - fp32-grade logits (error < 2^-21 |a||b|) at 3x the tensor work; uses a transient
+ * stream-ordered workspace and scores 262,144 rows per launch.  class_conf [c] float or NULL (= all ones, plain softmax).
  * pred_out [n] int32, conf_out [n] float, rowmax_out [n] float (logit_scale * max cosine) may
  * each be NULL.  labels [n] int64 + thresholds_host [n_thr] (HOST doubles) + table (device)
  * enable the fused binning; pass table = NULL to skip it.

@@ -304,18 +304,33 @@ def test_empty_inputs(cuda_lib):
     assert p.numel() == 0 and c.numel() == 0
 
 
-def test_wide_inputs_default_to_fp16_operands(cuda_lib):
-    """fp32 features are not rounded to bf16 behind the user's back: the default operand dtype for wide
-    inputs is fp16 (what the reference runs on the GPU), 8x finer than bf16 for unit-norm features."""
-    case = synth.make_case("fp32", 2000, 300, 150, 512, 5, 0.3, seed=4, rounding=lambda x: np.asarray(x, np.float32))
+@pytest.mark.parametrize("n,c,d", [(2000, 300, 512), (3000, 1000, 768), (1024, 49408, 512), (20000, 500, 128)])
+def test_fp32_features_split_precision_mode(cuda_lib, n, c, d, score_ctas):
+    """fp32 features that are NOT representable in 16 bits: the default (split-precision: fp16 hi/lo pairs,
+    3 MMAs per K step) must match the reference's fp32 path like the 16-bit path matches it on pre-rounded
+    inputs - labels exact outside the tie band, confidences within 1e-4 relative - where plainly rounding the
+    features to fp16 / bf16 does not."""
+    ident = lambda x: np.asarray(x, np.float32)
+    case = synth.make_case("fp32", n, c, max(1, c // 2), d, 5, 0.3, seed=n, rounding=ident)
+    cc = (0.95 + 0.05 * np.random.default_rng(1).random(c)).astype(np.float32)
+    pref, cref, gap = orc.score_chain(case.img, case.txt_tuned, cc, 100.0)
     dac = DistanseAwareCalibration()
-    dac.class_confidence = np.ones(300)
-    pred, conf = dac.predict_from_features(case.img, case.txt_tuned, 100.0)
-    pref, cref, gap = orc.score_chain(case.img, case.txt_tuned, None, 100.0)
-    ok = gap > 0.05                                        # fp16 rounding moves logits by ~1e-2
-    assert np.array_equal(pred[ok], pref[ok])
-    np.testing.assert_allclose(conf[ok], cref[ok], rtol=3e-2)
-    assert np.median(np.abs(conf[ok] - cref[ok]) / cref[ok]) < 2e-3
+    dac.class_confidence = cc.astype(np.float64)
+    pred, conf = dac.predict_from_features(case.img, case.txt_tuned, 100.0)            # default -> split precision
+    ok = gap > 2e-4
+    assert np.array_equal(pred[ok], pref[ok]) and (~ok).mean() < 5e-3
+    np.testing.assert_allclose(conf[ok], cref[ok], rtol=1e-4)
+    # fused binning + TS objective go through the same operands
+    table = native.new_table(10)
+    native.score_fused(dev(case.img), dev(case.txt_tuned), dev(cc), 100.0, dev(case.labels), tm.uniform_thresholds(10), table)
+    assert abs(tm.ece_from_table(native.table_to_numpy(table)) - orc.ece(cref, pref, case.labels, 10)) < 1e-5
+    if n <= 3000:
+        loss, grad = tempscaling.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, 4.6052)
+        lref, gref = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, 4.6052)
+        assert abs(loss - lref) <= 2e-5 * max(1.0, abs(lref)) and abs(grad - gref) <= 2e-5 * max(1.0, abs(gref))
+    # rounding the features instead is visibly worse (that is why it is not the default)
+    p16, c16 = dac.predict_from_features(case.img, case.txt_tuned, 100.0, operand_dtype=torch.bfloat16)
+    assert np.median(np.abs(c16[ok] - cref[ok]) / cref[ok]) > 20 * np.median(np.abs(conf[ok] - cref[ok]) / cref[ok])
 
 
 # ----------------------------------------------------------------------------- errors
