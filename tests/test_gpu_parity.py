@@ -339,8 +339,11 @@ def test_bad_arguments_fail_loudly(cuda_lib):
         native.score_fused(torch.zeros(8, 100, dtype=torch.bfloat16, device="cuda"),
                            torch.zeros(8, 100, dtype=torch.bfloat16, device="cuda"))         # D not a multiple of 64
     with pytest.raises(ValueError):
-        native.score_fused(torch.zeros(8, 64, dtype=torch.float32, device="cuda"),
-                           torch.zeros(8, 64, dtype=torch.float32, device="cuda"))           # fp32 operands
+        native.score_fused(torch.zeros(8, 64, dtype=torch.float64, device="cuda"),
+                           torch.zeros(8, 64, dtype=torch.float64, device="cuda"))           # fp64 operands
+    with pytest.raises(ValueError):
+        native.score_fused(torch.zeros(8, 64, dtype=torch.float16, device="cuda"),
+                           torch.zeros(8, 64, dtype=torch.bfloat16, device="cuda"))          # mixed operand dtypes
     with pytest.raises(ValueError):
         native.knn_l2(torch.zeros(4, 64, device="cuda"), torch.zeros(4, 64, device="cuda"), 99)
     with pytest.raises(Exception):
