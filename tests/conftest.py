@@ -15,6 +15,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real sm_100 GPU (run with -m gpu on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    """The C-ABI library is a build artefact (git-ignored): make sure it exists and matches the sources
+    before any test touches it (no-op when the stamp is current; nvcc cross-compiles without a GPU)."""
+    from clip_calibration_b200 import build as _build
+    _build.build()
+    _build.build_c_demo()
+    return _build.LIB
+
+
 @pytest.fixture(scope="session")
 def golden():
     def load(name):
