@@ -361,6 +361,14 @@ def main():
                              "note": "two-pass algorithm executes 4*N*C*D tensor flops (pass 1 max/argmax, pass 2 "
                                      "sum-exp); the north-star >=60 % target is read against this figure"},
                 "kernel_ms": k_ms, "kernel_ms_min": min(kern_ms), "kernel_share_of_step": k_ms * args.steps / ms_total}
+    if clocks and clocks.get("sm_mhz"):
+        # the hardware ceiling at the clock the power cap allowed: 148 SMs x 8192 dense bf16 flop/cycle/SM
+        hw = 148 * 8192 * clocks["sm_mhz"] * 1e6 / 1e12
+        roofline["executed"]["hw_peak_at_observed_clock"] = hw
+        roofline["executed"]["frac_of_hw_peak_at_observed_clock"] = exec_tf / hw
+        roofline["executed"]["why_above_cublas"] = (
+            "the measured peaks are cuBLAS bf16 GEMM rates under the same 1000 W cap, not the tensor pipe's limit; "
+            "ncu shows sm__pipe_tensor_cycles_active 99.8 % for this kernel (profiles/r01b_score_fused_ncu_raw.csv)")
 
     # ---------------- CPU baseline (bounded sample, this box's host cores)
     cpu = None

@@ -138,3 +138,18 @@ def test_reliability_bins_from_table():
     sel = conf >= 0.9
     assert abs(rb["accuracy"][9] - np.mean(pred[sel] == gt[sel])) < 1e-12
     assert abs(rb["confidence"][9] - np.mean(conf[sel].astype(np.float64))) < 1e-9
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference runs on host cores only (oracle port): check the line's contract here."""
+    import json, subprocess, sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["config"]["workload"].startswith("open-vocabulary") and d["metric"].startswith("calibrated images/sec")
