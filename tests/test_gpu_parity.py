@@ -290,6 +290,19 @@ def test_c_abi_from_plain_c(cuda_lib):
     assert "C ABI smoke: OK" in res.stdout
 
 
+def test_nearest_tokens_matches_cdist_argsort(cuda_lib):
+    """interpret_prompts/interpret_prompt.py:69-72 on the CUDA kNN: 16 context vectors vs a 49,408-token table."""
+    from clip_calibration_b200 import interpret
+    g = torch.Generator().manual_seed(0)
+    emb = torch.randn(49408, 512, generator=g) * 0.02
+    ctx = emb[torch.randint(0, 49408, (16,), generator=g)] + 0.01 * torch.randn(16, 512, generator=g)
+    idx, dist = interpret.nearest_tokens(ctx.numpy(), emb.numpy(), 5)
+    full = torch.cdist(ctx, emb)
+    ref_idx = torch.argsort(full, dim=1)[:, :5]
+    assert np.array_equal(idx, ref_idx.numpy())
+    np.testing.assert_allclose(dist, torch.gather(full, 1, ref_idx).numpy(), rtol=2e-5, atol=1e-6)
+
+
 def test_empty_inputs(cuda_lib):
     e_img = torch.zeros((0, 64), dtype=torch.bfloat16, device="cuda")
     txt = torch.zeros((5, 64), dtype=torch.bfloat16, device="cuda")
