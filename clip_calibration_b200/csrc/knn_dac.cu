@@ -195,7 +195,8 @@ int knn_l2_tensor(const float* ref, const float* query, int64_t nr, int64_t nq, 
 // tensor-core filter + exact verification when the problem is big enough to amortise it
 static int launch_knn(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k, int drop_first,
                       float* dist_out, int32_t* idx_out, cudaStream_t stream) {
-  const bool tc_ok = (d % 64 == 0) && d <= 1024 && nr >= 256 && nq >= 256 && nr * nq >= (1ll << 20);
+  // below ~64k (query, reference) pairs the exhaustive scan's single launch wins
+  const bool tc_ok = (d % 64 == 0) && d <= 1024 && nr >= 64 && nq >= 128 && nr * nq >= (1ll << 16);
   if (tc_ok) return knn_l2_tensor(ref, query, nr, nq, d, k, drop_first, dist_out, idx_out, stream);
   return launch_knn_exact(ref, query, nr, nq, d, k, drop_first, dist_out, idx_out, nullptr, nullptr, stream);
 }
