@@ -27,8 +27,7 @@ namespace ccal {
 constexpr int kTcBlockM = 128, kTcBlockN = 256, kTcBlockK = 64, kTcUmmaK = 16;
 constexpr int kTcQBytes = kTcBlockM * kTcBlockK * 2;     // 16 KB
 constexpr int kTcRBytes = kTcBlockN * kTcBlockK * 2;     // 32 KB
-constexpr int kTcStageBytes = 2 * kTcQBytes + 2 * kTcRBytes;   // 96 KB
-constexpr int kTcStages = 2;
+constexpr int kTcStages = 3;                              // barrier slots (pairs use 3 stages, single CTAs 2)
 constexpr int kTcThreads = 192;
 constexpr int kTcCtlBytes = 1024;
 
@@ -80,7 +79,9 @@ struct KnnTcParams {
   float* cand_cut;               // [nq] score of the worst kept candidate (-inf if the list is not full)
 };
 
-template <int KP>
+// kCtas = 2: CTA pairs (cta_group::2): each CTA owns 128 query rows and loads only half (128 rows) of every
+// reference tile; stage = {Qhi, Qlo, Rhi/2, Rlo/2} = 64 KB, 3 stages.  kCtas = 1: 96 KB stages, 2 stages.
+template <int KP, int kCtas>
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qlo,
               const __grid_constant__ CUtensorMap map_rhi, const __grid_constant__ CUtensorMap map_rlo,
@@ -90,17 +91,29 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
   const uint32_t op_base = (ptx::smem_u32(smem_dyn) + kTcCtlBytes + 1023u) & ~1023u;
   unsigned char* op_ptr = smem_dyn + (op_base - ptx::smem_u32(smem_dyn));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kRBytes = kTcRBytes / kCtas;                 // reference bytes this CTA loads per matrix per stage
+  constexpr int kRRows = kTcBlockN / kCtas;
+  constexpr int kStageBytes = 2 * kTcQBytes + 2 * kRBytes;
+  constexpr int kStages = kCtas == 2 ? 3 : 2;
+  constexpr int kTileRows = kTcBlockM * kCtas;
+  const uint32_t rank = (kCtas == 2) ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit = (kCtas == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = (int)gridDim.x / kCtas;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_qhi); ptx::prefetch_tensormap(&map_qlo);
     ptx::prefetch_tensormap(&map_rhi); ptx::prefetch_tensormap(&map_rlo);
     for (int i = 0; i < kTcStages; ++i) { ptx::mbar_init(&ctl->full[i], 1); ptx::mbar_init(&ctl->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&ctl->tmem_full[i], 1); ptx::mbar_init(&ctl->tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&ctl->tmem_full[i], 1); ptx::mbar_init(&ctl->tmem_empty[i], 4 * kCtas); }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) { ptx::tmem_alloc(&ctl->tmem_base, 512); ptx::tmem_relinquish(); }
+  if (warp == 1) {
+    if (kCtas == 2) { ptx::tmem_alloc_2sm(&ctl->tmem_base, 512); ptx::tmem_relinquish_2sm(); }
+    else { ptx::tmem_alloc(&ctl->tmem_base, 512); ptx::tmem_relinquish(); }
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
   const int NT = p.n_col_tiles, KB = p.kblocks;
@@ -108,58 +121,76 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
   if (warp == 0) {
     // TMA producer: whole warp loops, one elected lane issues (warp-uniform control flow)
     uint32_t stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x)
-      for (int nt = 0; nt < NT; ++nt)
+    for (int tile = unit; tile < p.n_row_tiles; tile += n_units) {
+      const int row0 = tile * kTileRows + (int)rank * kTcBlockM;
+      for (int nt = 0; nt < NT; ++nt) {
+        const int col0 = nt * kTcBlockN + (int)rank * kRRows;
         for (int kb = 0; kb < KB; ++kb) {
-          unsigned char* sp = op_ptr + (size_t)stage * kTcStageBytes;
+          unsigned char* sp = op_ptr + (size_t)stage * kStageBytes;
           ptx::mbar_wait(&ctl->empty[stage], phase ^ 1u);
           if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(&ctl->full[stage], kTcStageBytes);
-            ptx::tma_load_2d(sp, &map_qhi, &ctl->full[stage], kb * kTcBlockK, tile * kTcBlockM, ptx::kEvictNormal);
-            ptx::tma_load_2d(sp + kTcQBytes, &map_qlo, &ctl->full[stage], kb * kTcBlockK, tile * kTcBlockM, ptx::kEvictNormal);
-            ptx::tma_load_2d(sp + 2 * kTcQBytes, &map_rhi, &ctl->full[stage], kb * kTcBlockK, nt * kTcBlockN, ptx::kEvictLast);
-            ptx::tma_load_2d(sp + 2 * kTcQBytes + kTcRBytes, &map_rlo, &ctl->full[stage], kb * kTcBlockK, nt * kTcBlockN, ptx::kEvictLast);
-          }
-          __syncwarp();
-          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
-        }
-  } else if (warp == 1) {
-    // MMA issuer: whole warp waits, one elected lane issues 12 MMAs + commit per 64-feature block
-    uint32_t stage = 0, phase = 0, acc_it = 0;
-    for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x)
-      for (int nt = 0; nt < NT; ++nt, ++acc_it) {
-        const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-        ptx::mbar_wait(&ctl->tmem_empty[as], aph ^ 1u);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * kTcBlockN;
-        for (int kb = 0; kb < KB; ++kb) {
-          const uint32_t sp = op_base + stage * kTcStageBytes;
-          ptx::mbar_wait(&ctl->full[stage], phase);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint64_t qhi = ptx::make_kmajor_sw128_desc(sp), qlo = ptx::make_kmajor_sw128_desc(sp + kTcQBytes);
-            const uint64_t rhi = ptx::make_kmajor_sw128_desc(sp + 2 * kTcQBytes);
-            const uint64_t rlo = ptx::make_kmajor_sw128_desc(sp + 2 * kTcQBytes + kTcRBytes);
-#pragma unroll
-            for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k) {
-              const uint64_t o = (uint64_t)(k * 2);
-              ptx::umma_f16(d_tmem, qhi + o, rhi + o, p.idesc, (uint32_t)((kb | k) != 0));
-              ptx::umma_f16(d_tmem, qhi + o, rlo + o, p.idesc, 1u);
-              ptx::umma_f16(d_tmem, qlo + o, rhi + o, p.idesc, 1u);
+            if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[stage], kStageBytes * kCtas);
+            if (kCtas == 2) {
+              ptx::tma_load_2d_2sm(sp, &map_qhi, &ctl->full[stage], kb * kTcBlockK, row0, ptx::kEvictNormal);
+              ptx::tma_load_2d_2sm(sp + kTcQBytes, &map_qlo, &ctl->full[stage], kb * kTcBlockK, row0, ptx::kEvictNormal);
+              ptx::tma_load_2d_2sm(sp + 2 * kTcQBytes, &map_rhi, &ctl->full[stage], kb * kTcBlockK, col0, ptx::kEvictLast);
+              ptx::tma_load_2d_2sm(sp + 2 * kTcQBytes + kRBytes, &map_rlo, &ctl->full[stage], kb * kTcBlockK, col0, ptx::kEvictLast);
+            } else {
+              ptx::tma_load_2d(sp, &map_qhi, &ctl->full[stage], kb * kTcBlockK, row0, ptx::kEvictNormal);
+              ptx::tma_load_2d(sp + kTcQBytes, &map_qlo, &ctl->full[stage], kb * kTcBlockK, row0, ptx::kEvictNormal);
+              ptx::tma_load_2d(sp + 2 * kTcQBytes, &map_rhi, &ctl->full[stage], kb * kTcBlockK, col0, ptx::kEvictLast);
+              ptx::tma_load_2d(sp + 2 * kTcQBytes + kRBytes, &map_rlo, &ctl->full[stage], kb * kTcBlockK, col0, ptx::kEvictLast);
             }
-            ptx::umma_commit(&ctl->empty[stage]);
-            if (kb == KB - 1) ptx::umma_commit(&ctl->tmem_full[as]);
           }
           __syncwarp();
-          if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
+    }
+  } else if (warp == 1) {
+    // MMA issuer (pair leader): whole warp waits, one elected lane issues 12 MMAs + commit per 64-feature block
+    if (leader) {
+      uint32_t stage = 0, phase = 0, acc_it = 0;
+      for (int tile = unit; tile < p.n_row_tiles; tile += n_units)
+        for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+          const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+          ptx::mbar_wait(&ctl->tmem_empty[as], aph ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * kTcBlockN;
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint32_t sp = op_base + stage * kStageBytes;
+            ptx::mbar_wait(&ctl->full[stage], phase);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint64_t qhi = ptx::make_kmajor_sw128_desc(sp), qlo = ptx::make_kmajor_sw128_desc(sp + kTcQBytes);
+              const uint64_t rhi = ptx::make_kmajor_sw128_desc(sp + 2 * kTcQBytes);
+              const uint64_t rlo = ptx::make_kmajor_sw128_desc(sp + 2 * kTcQBytes + kRBytes);
+              auto mma = [&](uint64_t ad, uint64_t bd, uint32_t acc) {
+                if (kCtas == 2) ptx::umma_f16_2sm(d_tmem, ad, bd, p.idesc, acc); else ptx::umma_f16(d_tmem, ad, bd, p.idesc, acc);
+              };
+#pragma unroll
+              for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k) {
+                const uint64_t o = (uint64_t)(k * 2);
+                mma(qhi + o, rhi + o, (uint32_t)((kb | k) != 0));
+                mma(qhi + o, rlo + o, 1u);
+                mma(qlo + o, rhi + o, 1u);
+              }
+              if (kCtas == 2) ptx::umma_commit_2sm(&ctl->empty[stage]); else ptx::umma_commit(&ctl->empty[stage]);
+              if (kb == KB - 1) {
+                if (kCtas == 2) ptx::umma_commit_2sm(&ctl->tmem_full[as]); else ptx::umma_commit(&ctl->tmem_full[as]);
+              }
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+    }
   } else {
     const int quarter = warp & 3;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     uint32_t acc_it = 0;
-    for (int tile = blockIdx.x; tile < p.n_row_tiles; tile += gridDim.x) {
-      const long long row = (long long)tile * kTcBlockM + quarter * 32 + lane;
+    for (int tile = unit; tile < p.n_row_tiles; tile += n_units) {
+      const long long row = (long long)tile * kTileRows + (long long)rank * kTcBlockM + quarter * 32 + lane;
       float ts[KP];
       int ti[KP];
 #pragma unroll
@@ -198,7 +229,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[as]);
+        if (lane == 0) {
+          if (kCtas == 2) ptx::mbar_arrive_cluster(&ctl->tmem_empty[as], 0u); else ptx::mbar_arrive(&ctl->tmem_empty[as]);
+        }
       }
       if (row < p.nq) {
 #pragma unroll
@@ -209,9 +242,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
   }
   __syncwarp();
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+  if (warp == 1) {
+    if (kCtas == 2) ptx::tmem_dealloc_2sm(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------------------- 3
@@ -297,24 +332,46 @@ static int run_tc(const float* ref, const float* query, int64_t nr, int64_t nq, 
                   int* redo_list, int* redo_count, cudaStream_t stream) {
   split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(query, nq, d, qhi, qlo, qhn, nullptr);
   note_launch();
+  // CTA pairs when every pair gets at least one 256-row tile on most SMs; single CTAs for small query sets
+  const int sms = num_sms();
+  const int ctas = (nq >= (int64_t)kTcBlockM * 2 * (sms / 4)) ? 2 : 1;
   CUtensorMap mqh, mql, mrh, mrl;
   int rc;
   if ((rc = make_map(&mqh, qhi, nq, d, kTcBlockM, CCAL_BF16))) return rc;
   if ((rc = make_map(&mql, qlo, nq, d, kTcBlockM, CCAL_BF16))) return rc;
-  if ((rc = make_map(&mrh, rhi, nr, d, kTcBlockN, CCAL_BF16))) return rc;
-  if ((rc = make_map(&mrl, rlo, nr, d, kTcBlockN, CCAL_BF16))) return rc;
+  if ((rc = make_map(&mrh, rhi, nr, d, kTcBlockN / ctas, CCAL_BF16))) return rc;
+  if ((rc = make_map(&mrl, rlo, nr, d, kTcBlockN / ctas, CCAL_BF16))) return rc;
   KnnTcParams p{};
   p.nq = nq; p.nr = nr;
   p.kblocks = d / kTcBlockK;
   p.n_col_tiles = (int)((nr + kTcBlockN - 1) / kTcBlockN);
-  p.n_row_tiles = (int)((nq + kTcBlockM - 1) / kTcBlockM);
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcBlockN >> 3) << 17) | ((uint32_t)(kTcBlockM >> 4) << 24);
+  const int tile_rows = kTcBlockM * ctas;
+  p.n_row_tiles = (int)((nq + tile_rows - 1) / tile_rows);
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcBlockN >> 3) << 17) | ((uint32_t)(tile_rows >> 4) << 24);
   p.r_half_norm2 = rhn; p.cand_idx = cand; p.cand_cut = cut;
-  const size_t smem = kTcCtlBytes + 1024 + (size_t)kTcStages * kTcStageBytes;
-  auto kern = knn_tc_kernel<KP>;
-  CCAL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int sms = num_sms();
-  kern<<<p.n_row_tiles < sms ? p.n_row_tiles : sms, kTcThreads, smem, stream>>>(mqh, mql, mrh, mrl, p);
+  const size_t smem = kTcCtlBytes + 1024 + (ctas == 2 ? (size_t)3 * (2 * kTcQBytes + kTcRBytes) : (size_t)2 * (2 * kTcQBytes + 2 * kTcRBytes));
+  const int units = sms / ctas;
+  const int grid = (p.n_row_tiles < units ? p.n_row_tiles : units) * ctas;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  if (ctas == 2) {
+    auto kern = knn_tc_kernel<KP, 2>;
+    CCAL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg.numAttrs = 1;
+    CCAL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mqh, mql, mrh, mrl, p));
+  } else {
+    auto kern = knn_tc_kernel<KP, 1>;
+    CCAL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cfg.numAttrs = 0;
+    CCAL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mqh, mql, mrh, mrl, p));
+  }
   note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   knn_verify_kernel<KP><<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(ref, query, nr, nq, d, k, drop_first, cand, cut, qhn,
