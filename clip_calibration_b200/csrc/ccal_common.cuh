@@ -37,6 +37,35 @@ void note_launch(int n = 1);   // process-wide count of kernels this library lau
 // {64 features, box_rows}, 128-byte swizzle, zero fill out of range (defined in score_fused.cu).
 int make_map(CUtensorMap* map, const void* base, long long rows, int d, int box_rows, int dtype);
 
+// Transient, stream-ordered workspace (cudaMallocAsync); released on every exit path.
+struct AsyncWorkspace {
+  unsigned char* ptr = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaError_t alloc(size_t bytes, cudaStream_t s) {
+    stream = s;
+    // keep freed workspace cached in the device's default pool instead of returning it to the driver at
+    // every synchronisation (the default release threshold is 0, which costs milliseconds per call)
+    static thread_local int tuned_dev = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev != tuned_dev) {
+      cudaMemPool_t pool;
+      if ((e = cudaDeviceGetDefaultMemPool(&pool, dev)) != cudaSuccess) return e;
+      unsigned long long keep = ~0ull;
+      if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
+      tuned_dev = dev;
+    }
+    return cudaMallocAsync(reinterpret_cast<void**>(&ptr), bytes, s);
+  }
+  ~AsyncWorkspace() {
+    if (ptr) cudaFreeAsync(ptr, stream);
+  }
+  AsyncWorkspace() = default;
+  AsyncWorkspace(const AsyncWorkspace&) = delete;
+  AsyncWorkspace& operator=(const AsyncWorkspace&) = delete;
+};
+
 // Thresholds are given as doubles (np.linspace edges are float64 and np.digitize compares
 // in double).  For a float key x and a double threshold t:  x >= t  <=>  x >= ceil_f32(t),
 // the smallest float32 that is >= t.  So the device compares floats only.

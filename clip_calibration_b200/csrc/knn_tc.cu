@@ -401,22 +401,9 @@ int knn_l2_tensor(const float* ref, const float* query, int64_t nr, int64_t nq, 
   const size_t o_qhi = take((size_t)chunk * d * bf), o_qlo = take((size_t)chunk * d * bf), o_qhn = take((size_t)chunk * 4);
   const size_t o_cand = take((size_t)chunk * KP * 4), o_cut = take((size_t)chunk * 4);
   const size_t o_list = take((size_t)chunk * 4), o_cnt = take(256), o_rmax = take(256);
-  // keep freed workspace cached in the device's default pool instead of returning it to the driver
-  // at every synchronisation (the default release threshold is 0)
-  {
-    static thread_local int tuned_dev = -1;
-    int dev = 0;
-    CCAL_CUDA_OK(cudaGetDevice(&dev));
-    if (dev != tuned_dev) {
-      cudaMemPool_t pool;
-      CCAL_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
-      unsigned long long keep = ~0ull;
-      CCAL_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-      tuned_dev = dev;
-    }
-  }
-  unsigned char* ws = nullptr;
-  CCAL_CUDA_OK(cudaMallocAsync((void**)&ws, off, stream));
+  AsyncWorkspace workspace;
+  CCAL_CUDA_OK(workspace.alloc(off, stream));
+  unsigned char* ws = workspace.ptr;
   __nv_bfloat16* rhi = (__nv_bfloat16*)(ws + o_rhi);
   __nv_bfloat16* rlo = (__nv_bfloat16*)(ws + o_rlo);
   float* rhn = (float*)(ws + o_rhn);
@@ -444,7 +431,6 @@ int knn_l2_tensor(const float* ref, const float* query, int64_t nr, int64_t nq, 
       fprintf(stderr, "ccal knn_l2_tensor: nr=%lld nq=%lld d=%d k=%d KP=%d unproven rows=%d\n", (long long)nr, (long long)m, d, k, KP, h);
     }
   }
-  cudaFreeAsync(ws, stream);
   return rc;
 }
 

@@ -589,8 +589,9 @@ static int run_fused(int mode, const void* img, const void* txt, int64_t n, int 
   const size_t o_thi = take((size_t)c * d * 2), o_tlo = take((size_t)c * d * 2);
   const size_t o_ihi = take((size_t)chunk * d * 2), o_ilo = take((size_t)chunk * d * 2);
   const size_t o_max = take(8), o_exp = take(8);
-  unsigned char* ws = nullptr;
-  CCAL_CUDA_OK(cudaMallocAsync((void**)&ws, off, stream));
+  AsyncWorkspace workspace;
+  CCAL_CUDA_OK(workspace.alloc(off, stream));
+  unsigned char* ws = workspace.ptr;
   unsigned int* maxbits = (unsigned int*)(ws + o_max);
   int* exps = (int*)(ws + o_exp);
   const float* fimg = (const float*)img;
@@ -619,8 +620,7 @@ static int run_fused(int mode, const void* img, const void* txt, int64_t n, int 
     if (pc.labels) pc.labels += q0;
     rc = launch_fused(mode, ws + o_ihi, ws + o_thi, ws + o_ilo, ws + o_tlo, m, c, d, CCAL_F16, pc, thr, stream);
   }
-  cudaFreeAsync(ws, stream);
-  CCAL_CUDA_OK(cudaGetLastError());
+  if (rc == CCAL_OK) CCAL_CUDA_OK(cudaGetLastError());
   return rc;
 }
 
