@@ -250,6 +250,8 @@ def main():
         return
 
     import torch.distributed as dist
+    from clip_calibration_b200 import build as _build
+    _build.build()                         # no-op when libccal.so matches the sources (it normally travels pre-built)
     from clip_calibration_b200 import _lib, native, pipeline
     from clip_calibration_b200 import table_math as tm
 

@@ -47,12 +47,28 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+def _up_to_date(digest: str) -> bool:
+    if os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:
-            if fh.read().strip() == digest:
-                return LIB
+            return fh.read().strip() == digest
+    return False
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libccal.so if it is missing or older than the sources.  Safe to call from several
+    processes at once (torchrun ranks): an exclusive file lock serialises the compile."""
+    import fcntl
+    digest = _digest()
+    if not force and _up_to_date(digest):
+        return LIB
+    with open(os.path.join(HERE, ".libccal.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and _up_to_date(digest):          # another process built it while we waited
+            return LIB
+        return _compile(digest, verbose)
+
+
+def _compile(digest: str, verbose: bool) -> str:
     cmd = [_nvcc()] + NVCC_FLAGS
     if verbose:
         cmd += ["-Xptxas", "-v"]
