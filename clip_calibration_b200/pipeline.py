@@ -46,6 +46,7 @@ class CalibratedScorer:
         self.group = group          # None = default process group (if initialised); False = never reduce
         self.table = native.new_table(self.n_bins, device=self.device)
         self._copy_stream = None
+        self._pending_img, self._pending_lab, self._pending_rows = [], [], 0
 
     # ------------------------------------------------------------------ construction helpers
     def _features(self, x) -> torch.Tensor:
@@ -68,6 +69,7 @@ class CalibratedScorer:
     # ------------------------------------------------------------------ scoring
     def reset(self):
         self.table.zero_()
+        self._pending_img, self._pending_lab, self._pending_rows = [], [], 0
 
     def score(self, image_features, labels=None, accumulate: bool = True):
         """Device-resident shard -> (pred, conf); with labels the shard is also binned into the
@@ -80,6 +82,27 @@ class CalibratedScorer:
         pred, conf, _ = native.score_fused(img, self.txt, self.class_conf, self.logit_scale, labels,
                                            self.thresholds if use_table else None, self.table if use_table else None)
         return pred, conf
+
+    def add(self, image_features, labels, flush_rows: int = 32768) -> None:
+        """Per-batch entry point for an evaluation loop (the reference feeds 100 images at a time,
+        base_learner.py:84-88).  A 100-row launch would occupy ONE of the 148 SMs, so batches are parked on
+        the device (operand dtype, no host copies) and scored together once `flush_rows` have arrived;
+        `summary()` / `reduced_table()` flush the remainder.  Only the bin table is produced on this path."""
+        img = self._features(image_features)
+        lab = (labels if isinstance(labels, torch.Tensor) else torch.from_numpy(np.asarray(labels)))
+        self._pending_img.append(img)
+        self._pending_lab.append(lab.to(device=self.device, dtype=torch.int64))
+        self._pending_rows += int(img.shape[0])
+        if self._pending_rows >= flush_rows:
+            self.flush()
+
+    def flush(self) -> None:
+        if self._pending_rows:
+            img = torch.cat(self._pending_img) if len(self._pending_img) > 1 else self._pending_img[0]
+            lab = torch.cat(self._pending_lab) if len(self._pending_lab) > 1 else self._pending_lab[0]
+            self._pending_img, self._pending_lab, self._pending_rows = [], [], 0
+            native.score_fused(img, self.txt, self.class_conf, self.logit_scale, lab, self.thresholds, self.table,
+                               want_pred=False, want_conf=False)
 
     def accumulate_host(self, image_features: torch.Tensor, labels: torch.Tensor, chunk_rows: int = 131072,
                         keep_outputs: bool = False, ramp: bool = True):
@@ -136,6 +159,7 @@ class CalibratedScorer:
     def reduced_table(self) -> np.ndarray:
         """The bin table summed over all ranks of `group` (one NCCL all-reduce of
         3*(n_bins+1) int64 on the compute stream), as a host uint64 array."""
+        self.flush()
         t = self.table
         if self.group is not False and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size(self.group) > 1:

@@ -249,6 +249,11 @@ def test_end_to_end_pipeline_and_host_path(cuda_lib, golden, synth_case):
     host = torch.from_numpy(case.img).to(torch.bfloat16).pin_memory()
     scorer.accumulate_host(host, torch.from_numpy(case.labels).pin_memory(), chunk_rows=8192)
     assert np.array_equal(scorer.reduced_table(), device_table)
+    # the per-batch loop of the reference (100 images at a time), buffered on the device
+    scorer.reset()
+    for lo in range(0, len(case.labels), 100):
+        scorer.add(case.img[lo:lo + 100], case.labels[lo:lo + 100], flush_rows=16384)
+    assert np.array_equal(scorer.reduced_table(), device_table)
     # shards add up exactly (what the multi-GPU all-reduce relies on)
     scorer.reset()
     for r in range(3):
