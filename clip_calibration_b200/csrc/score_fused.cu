@@ -501,7 +501,10 @@ static int launch_fused(int mode, const void* img, const void* txt, const void* 
   const int avail = kSmemLimit - kCtlBytes - 1024;          // after control block and alignment slack
   const int b_bytes = kBTileBytes / ctas;
   const int parts = split ? 2 : 1;
-  const bool resident = !split && (p.kblocks * kASlabBytes + 2 * kBTileBytes) <= avail;
+  bool resident = !split && (p.kblocks * kASlabBytes + 2 * kBTileBytes) <= avail;
+  if (const char* e = getenv("CCAL_SCORE_RESIDENT")) {      // development aid: force the resident layout when >= 2 stages fit
+    if (e[0] == '1' && !split && (p.kblocks * kASlabBytes + 2 * b_bytes) <= avail) resident = true;
+  }
   int stages = resident ? (avail - p.kblocks * kASlabBytes) / b_bytes : avail / (parts * (kASlabBytes + b_bytes));
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
