@@ -70,6 +70,15 @@ struct ScoreParams {
   unsigned long long* table;
   float* row_ws;                       // kMode 1: [2*n] per-row loss / gradient terms
   const int* split_exps;               // kSplit: {e_img, e_txt}: operands were pre-scaled by 2^e before the fp16 split
+  // Column-split mode (few image rows, many classes): work unit = (row tile, column range).  Launched once
+  // with pass_lo = pass_hi = 0 (partial max / argmax per unit -> part_max / part_arg), then, after a tiny
+  // combine, once with pass_lo = pass_hi = 1 (partial sum-exp at the known row max / pred -> part_sum).
+  int n_splits, pass_lo, pass_hi;
+  float* part_max;                     // [n, n_splits] raw dot-product maxima
+  int* part_arg;                       // [n, n_splits]
+  float* part_sum;                     // [n, n_splits]
+  const float* row_max_in;             // [n] raw dot-product row max (pass 2 of the split mode)
+  const int* row_pred_in;              // [n]
 };
 
 
@@ -176,17 +185,20 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
 
   const int NT = p.n_col_tiles;
   const int KB = p.kblocks;
+  const int S = p.n_splits;                       // column ranges per row tile (1 = the normal mode)
+  const int n_work = p.n_row_tiles * S;
 
   if (warp == 0) {
     // ================================================================ TMA producer (whole warp loops, one
     // elected lane issues; keeping the control flow warp-uniform keeps the issue path short)
     uint32_t stage = 0, phase = 0, ti = 0;
-    for (int tile = unit; tile < p.n_row_tiles; tile += n_units, ++ti) {
+    for (int u = unit; u < n_work; u += n_units, ++ti) {
+      const int tile = u / S, nt_begin = (u % S) * NT / S, nt_end = ((u % S) + 1) * NT / S;
       const int row0 = tile * kTileRows + (int)rank * kBlockM;
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int nt = 0; nt < NT; ++nt) {
+      for (int pass = p.pass_lo; pass <= p.pass_hi; ++pass) {
+        for (int nt = nt_begin; nt < nt_end; ++nt) {
           const int col0 = nt * kBlockN + (int)rank * kBRows;
-          const bool load_a = kResident && pass == 0 && nt == 0;
+          const bool load_a = kResident && pass == p.pass_lo && nt == nt_begin;
           for (int kb = 0; kb < KB; ++kb) {
             unsigned char* sp = ring_ptr + (size_t)stage * stage_bytes;
             // slab kb of the previous row tile must have been consumed by its last MMA
@@ -235,16 +247,17 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
     if (leader) {
       uint32_t stage = 0, phase = 0, acc_it = 0, ti = 0;
       const uint32_t ring_base = op_base + (kResident ? (uint32_t)KB * kASlabBytes : 0u);
-      for (int tile = unit; tile < p.n_row_tiles; tile += n_units, ++ti) {
-        for (int pass = 0; pass < 2; ++pass) {
-          for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+      for (int u = unit; u < n_work; u += n_units, ++ti) {
+        const int nt_begin = (u % S) * NT / S, nt_end = ((u % S) + 1) * NT / S;
+        for (int pass = p.pass_lo; pass <= p.pass_hi; ++pass) {
+          for (int nt = nt_begin; nt < nt_end; ++nt, ++acc_it) {
             const uint32_t as = acc_it & 1u;
             const uint32_t aph = (acc_it >> 1) & 1u;
             ptx::mbar_wait(&ctl->tmem_empty[as], aph ^ 1u);      // epilogue(s) have drained this stage
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * kBlockN;
-            const bool first_use_of_a = kResident && pass == 0 && nt == 0;
-            const bool last_use_of_a = kResident && pass == 1 && nt == NT - 1;
+            const bool first_use_of_a = kResident && pass == p.pass_lo && nt == nt_begin;
+            const bool last_use_of_a = kResident && pass == p.pass_hi && nt == nt_end - 1;
             for (int kb = 0; kb < KB; ++kb) {
               const uint32_t sp = ring_base + stage * stage_bytes;
               if (first_use_of_a) ptx::mbar_wait(&ctl->a_full[kb], ti & 1u);
@@ -299,13 +312,15 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
         else ptx::mbar_arrive(&ctl->tmem_empty[as]);
       }
     };
-    for (int tile = unit; tile < p.n_row_tiles; tile += n_units) {
+    for (int u = unit; u < n_work; u += n_units) {
+      const int tile = u / S, split = u % S, nt_begin = split * NT / S, nt_end = (split + 1) * NT / S;
       const long long row = (long long)tile * kTileRows + (long long)rank * kBlockM + quarter * 32 + lane;
       const bool row_ok = row < p.n;
       // ---------------- pass 1: running max / first argmax of the raw dot products
       float m = -CUDART_INF_F;
       int arg = 0;
-      for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+      if (p.pass_lo == 0)
+      for (int nt = nt_begin; nt < nt_end; ++nt, ++acc_it) {
         const uint32_t as = acc_it & 1u;
         ptx::mbar_wait(&ctl->tmem_full[as], (acc_it >> 1) & 1u);
         ptx::tc_fence_after();
@@ -320,6 +335,11 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
         }
         release_acc(as);
       }
+      if (p.pass_hi == 0) {                       // column-split mode, first launch: partial (max, argmax) only
+        if (row_ok) { p.part_max[row * S + split] = m; p.part_arg[row * S + split] = arg; }
+        continue;
+      }
+      if (p.pass_lo == 1 && row_ok) { m = p.row_max_in[row]; arg = p.row_pred_in[row]; }
       // ---------------- pass 2: sum of exp at the predicted class's multiplier
       float cc = 1.0f;
       if (kMode == 0 && p.class_conf != nullptr) cc = __ldg(p.class_conf + arg);
@@ -327,7 +347,7 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
       const float b2 = m * a2;
       float sum = 0.f, wsum = 0.f, zy = 0.f;
       const int label = (kMode == 1 && row_ok) ? (int)p.labels[row] : -1;
-      for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+      for (int nt = nt_begin; nt < nt_end; ++nt, ++acc_it) {
         const uint32_t as = acc_it & 1u;
         ptx::mbar_wait(&ctl->tmem_full[as], (acc_it >> 1) & 1u);
         ptx::tc_fence_after();
@@ -348,6 +368,10 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
           }
         }
         release_acc(as);
+      }
+      if (S > 1) {                                // column-split mode, second launch: partial sum only
+        if (row_ok) p.part_sum[row * S + split] = sum;
+        continue;
       }
       // ---------------- per-row results
       if (kMode == 0) {
@@ -445,6 +469,70 @@ int make_map(CUtensorMap* map, const void* base, long long rows, int d, int box_
   return CCAL_OK;
 }
 
+// ---- column-split mode glue (few rows, many classes) -----------------------------------------------
+// combine the per-range (max, first argmax): ranges are in increasing class order, so on equal maxima the
+// lower range wins (first-max semantics)
+__global__ void __launch_bounds__(256)
+split_combine_max_kernel(const float* __restrict__ part_max, const int* __restrict__ part_arg, long long n, int S,
+                         float* __restrict__ row_max, int* __restrict__ row_pred) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  float m = part_max[row * S];
+  int a = part_arg[row * S];
+  for (int s = 1; s < S; ++s) {
+    const float v = part_max[row * S + s];
+    if (v > m) { m = v; a = part_arg[row * S + s]; }
+  }
+  row_max[row] = m;
+  row_pred[row] = a;
+}
+
+// sum the per-range partial sums in a fixed order, emit (pred, conf, rowmax) and bin
+__global__ void __launch_bounds__(256)
+split_finish_kernel(const float* __restrict__ part_sum, const float* __restrict__ row_max, const int* __restrict__ row_pred,
+                    long long n, int S, float scale, const int* __restrict__ split_exps, int* __restrict__ pred_out,
+                    float* __restrict__ conf_out, float* __restrict__ rowmax_out, const long long* __restrict__ labels,
+                    const __grid_constant__ ThrBlock thr, int n_thr, unsigned long long* __restrict__ table) {
+  __shared__ BinCell cells[CCAL_MAX_THRESHOLDS + 1];
+  __shared__ float s_thr[CCAL_MAX_THRESHOLDS + 1];
+  for (int i = threadIdx.x; i <= CCAL_MAX_THRESHOLDS; i += blockDim.x) {
+    cells[i] = BinCell{0u, 0u, 0ull};
+    s_thr[i] = i < n_thr ? thr.t[i] : CUDART_INF_F;
+  }
+  __syncthreads();
+  if (split_exps) scale *= exp2f(-(float)(split_exps[0] + split_exps[1]));
+  const long long n_round = ((n + 31) / 32) * 32;
+  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < n_round;
+       row += (long long)gridDim.x * blockDim.x) {
+    const bool ok = row < n;
+    float conf = 1.f;
+    int pred = 0;
+    if (ok) {
+      float sum = 0.f;
+      for (int s = 0; s < S; ++s) sum += part_sum[row * S + s];
+      conf = 1.0f / sum;
+      pred = row_pred[row];
+      if (pred_out) pred_out[row] = pred;
+      if (conf_out) conf_out[row] = conf;
+      if (rowmax_out) rowmax_out[row] = row_max[row] * scale;
+    }
+    if (table != nullptr) {
+      const bool correct = ok && ((long long)pred == labels[row]);
+      warp_bin_add(cells, bin_of(conf, s_thr, n_thr), correct, conf_to_fx(conf), ok);
+    }
+  }
+  __syncthreads();
+  if (table != nullptr)
+    for (int i = threadIdx.x; i <= n_thr; i += blockDim.x) {
+      const BinCell cell = cells[i];
+      if (cell.count) {
+        atomicAdd(&table[3 * i + 0], (unsigned long long)cell.count);
+        atomicAdd(&table[3 * i + 1], (unsigned long long)cell.correct);
+        atomicAdd(&table[3 * i + 2], cell.sum_fx);
+      }
+    }
+}
+
 template <int kCtas, bool kResident, int kMode, bool kSplit>
 static int launch_variant(const CUtensorMap& mi, const CUtensorMap& mt, const CUtensorMap& mi_lo, const CUtensorMap& mt_lo,
                           const ScoreParams& p, const ThrBlock& thr, int grid, size_t smem, cudaStream_t stream) {
@@ -481,7 +569,18 @@ static int choose_ctas(int64_t n) {
 static int launch_fused(int mode, const void* img, const void* txt, const void* img_lo, const void* txt_lo, int64_t n,
                         int c, int d, int dtype, ScoreParams p, const ThrBlock& thr, cudaStream_t stream) {
   const bool split = img_lo != nullptr;
-  const int ctas = choose_ctas(n);
+  int ctas = choose_ctas(n);
+  // Column-split mode: when the image rows cannot fill the SMs but the vocabulary is large, every row tile is
+  // cut into S class ranges (S work units per tile) and the kernel runs once per pass with tiny combines between.
+  const int sms_all = num_sms();
+  const int tiles128 = (int)((n + kBlockM - 1) / kBlockM);
+  const int col_tiles = (c + kBlockN - 1) / kBlockN;
+  int S = 1;
+  if (mode == 0 && col_tiles >= 4 && tiles128 * 2 <= sms_all && !getenv("CCAL_SCORE_NOSPLIT")) {
+    S = sms_all / tiles128;
+    if (S > col_tiles) S = col_tiles;
+    if (S > 1) ctas = 1;
+  }
   CUtensorMap map_img, map_txt, map_img_lo, map_txt_lo;
   int rc;
   if ((rc = make_map(&map_img, img, n, d, kBlockM, dtype))) return rc;
@@ -512,20 +611,51 @@ static int launch_fused(int mode, const void* img, const void* txt, const void* 
                       (resident ? (size_t)p.kblocks * kASlabBytes + (size_t)stages * b_bytes
                                 : (size_t)stages * parts * (kASlabBytes + b_bytes));
   const int units = num_sms() / ctas;
-  const int grid = (p.n_row_tiles < units ? p.n_row_tiles : units) * ctas;
-#define CCAL_LAUNCH(C, R, M, S) \
-  launch_variant<C, R, M, S>(map_img, map_txt, map_img_lo, map_txt_lo, p, thr, grid, smem, stream)
-  if (split) {
-    if (ctas == 2) return mode == 0 ? CCAL_LAUNCH(2, false, 0, true) : CCAL_LAUNCH(2, false, 1, true);
-    return mode == 0 ? CCAL_LAUNCH(1, false, 0, true) : CCAL_LAUNCH(1, false, 1, true);
-  }
-  if (ctas == 2) {
-    if (mode == 0) return resident ? CCAL_LAUNCH(2, true, 0, false) : CCAL_LAUNCH(2, false, 0, false);
-    return resident ? CCAL_LAUNCH(2, true, 1, false) : CCAL_LAUNCH(2, false, 1, false);
-  }
-  if (mode == 0) return resident ? CCAL_LAUNCH(1, true, 0, false) : CCAL_LAUNCH(1, false, 0, false);
-  return resident ? CCAL_LAUNCH(1, true, 1, false) : CCAL_LAUNCH(1, false, 1, false);
+  const int n_work = p.n_row_tiles * S;
+  const int grid = (n_work < units ? n_work : units) * ctas;
+  p.n_splits = S; p.pass_lo = 0; p.pass_hi = 1;
+  auto launch = [&](const ScoreParams& q) -> int {
+#define CCAL_LAUNCH(C, R, M, SP) \
+  launch_variant<C, R, M, SP>(map_img, map_txt, map_img_lo, map_txt_lo, q, thr, grid, smem, stream)
+    if (split) {
+      if (ctas == 2) return mode == 0 ? CCAL_LAUNCH(2, false, 0, true) : CCAL_LAUNCH(2, false, 1, true);
+      return mode == 0 ? CCAL_LAUNCH(1, false, 0, true) : CCAL_LAUNCH(1, false, 1, true);
+    }
+    if (ctas == 2) {
+      if (mode == 0) return resident ? CCAL_LAUNCH(2, true, 0, false) : CCAL_LAUNCH(2, false, 0, false);
+      return resident ? CCAL_LAUNCH(2, true, 1, false) : CCAL_LAUNCH(2, false, 1, false);
+    }
+    if (mode == 0) return resident ? CCAL_LAUNCH(1, true, 0, false) : CCAL_LAUNCH(1, false, 0, false);
+    return resident ? CCAL_LAUNCH(1, true, 1, false) : CCAL_LAUNCH(1, false, 1, false);
 #undef CCAL_LAUNCH
+  };
+  if (S == 1) return launch(p);
+
+  // ---- column-split orchestration: pass 1 per range -> combine -> pass 2 per range -> finish
+  AsyncWorkspace workspace;
+  const size_t per = ((size_t)n * S * 4 + 255) & ~(size_t)255, per_row = ((size_t)n * 4 + 255) & ~(size_t)255;
+  CCAL_CUDA_OK(workspace.alloc(3 * per + 2 * per_row, stream));
+  float* part_max = (float*)workspace.ptr;
+  int* part_arg = (int*)(workspace.ptr + per);
+  float* part_sum = (float*)(workspace.ptr + 2 * per);
+  float* row_max = (float*)(workspace.ptr + 3 * per);
+  int* row_pred = (int*)(workspace.ptr + 3 * per + per_row);
+  ScoreParams q = p;
+  q.pass_lo = q.pass_hi = 0;
+  q.part_max = part_max; q.part_arg = part_arg;
+  if ((rc = launch(q))) return rc;
+  const int rows_grid = (int)((n + 255) / 256);
+  split_combine_max_kernel<<<rows_grid, 256, 0, stream>>>(part_max, part_arg, (long long)n, S, row_max, row_pred);
+  note_launch();
+  q.pass_lo = q.pass_hi = 1;
+  q.row_max_in = row_max; q.row_pred_in = row_pred; q.part_sum = part_sum;
+  if ((rc = launch(q))) return rc;
+  split_finish_kernel<<<rows_grid < 4 * sms_all ? rows_grid : 4 * sms_all, 256, 0, stream>>>(
+      part_sum, row_max, row_pred, (long long)n, S, p.scale, p.split_exps, p.pred_out, p.conf_out, p.rowmax_out, p.labels, thr,
+      p.n_thr, p.table);
+  note_launch();
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
 }
 
 // ---- fp32 features: x * 2^e = hi + lo in fp16, e chosen per matrix so that max|x| * 2^e is in [2^9, 2^10)

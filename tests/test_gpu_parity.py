@@ -233,6 +233,33 @@ def test_fused_scoring_ragged_shapes_fp16_and_bf16(cuda_lib, n, c, d, score_ctas
         check_scoring(case, cc, pref, cref, gap, ece_ref, counts, dtype)
 
 
+@pytest.mark.parametrize("n,c,d,dtype", [(100, 49408, 512, torch.bfloat16), (1, 3000, 64, torch.float16), (1000, 21841, 768, torch.bfloat16),
+                                         (4097, 5000, 512, torch.bfloat16), (300, 2049, 128, torch.float32)])
+def test_column_split_mode_for_small_batches(cuda_lib, n, c, d, dtype, monkeypatch):
+    """Few image rows x a large vocabulary (the reference's 100-image batches, serving-style queries): every
+    row tile is cut into class ranges so that all SMs work on it.  Same labels as the unsplit kernel and the
+    oracle, confidences to rounding, identical fused bin table semantics."""
+    rounding = {torch.bfloat16: synth.round_to_bf16, torch.float16: synth.round_to_fp16,
+                torch.float32: lambda x: np.asarray(x, np.float32)}[dtype]
+    case = synth.make_case("small", n, c, max(1, c // 2), d, 5, 0.3, seed=n + c, rounding=rounding)
+    cc = (0.95 + 0.05 * np.random.default_rng(c).random(c)).astype(np.float32)
+    img, txt, ccd, lab = dev(case.img, dtype), dev(case.txt_tuned, dtype), dev(cc), dev(case.labels)
+    thr = tm.uniform_thresholds(10)
+    t_split, t_plain = native.new_table(10), native.new_table(10)
+    p1, c1, r1 = native.score_fused(img, txt, ccd, 100.0, lab, thr, t_split, want_rowmax=True)
+    monkeypatch.setenv("CCAL_SCORE_NOSPLIT", "1")
+    p0, c0, r0 = native.score_fused(img, txt, ccd, 100.0, lab, thr, t_plain, want_rowmax=True)
+    monkeypatch.delenv("CCAL_SCORE_NOSPLIT")
+    assert torch.equal(p1, p0) and torch.equal(r1, r0)
+    torch.testing.assert_close(c1, c0, rtol=1e-5, atol=0)
+    pref, cref, gap = orc.score_chain(case.img, case.txt_tuned, cc, 100.0)
+    ok = gap > (2e-4 if dtype == torch.float32 else TIE_GAP)
+    assert np.array_equal(p1.cpu().numpy()[ok], pref[ok])
+    np.testing.assert_allclose(c1.cpu().numpy()[ok], cref[ok], rtol=1e-4)
+    tab = native.table_to_numpy(t_split)
+    assert np.array_equal(tab, orc.bin_table(c1.cpu().numpy(), p1.cpu().numpy(), case.labels, thr))
+
+
 def test_end_to_end_pipeline_and_host_path(cuda_lib, golden, synth_case):
     g, case = golden("imagenet"), synth_case("imagenet")
     scorer = pipeline.CalibratedScorer.from_dac(case.base_zs, case.txt_zs, case.base_tuned, case.txt_tuned, k=5,
