@@ -76,7 +76,7 @@ struct ScoreParams {
   int n_splits, pass_lo, pass_hi;
   float* part_max;                     // [n, n_splits] raw dot-product maxima
   int* part_arg;                       // [n, n_splits]
-  float* part_sum;                     // [n, n_splits]
+  float* part_sum;                     // [n, n_col_tiles] per-tile partial sums (canonical order)
   const float* row_max_in;             // [n] raw dot-product row max (pass 2 of the split mode)
   const int* row_pred_in;              // [n]
 };
@@ -352,13 +352,17 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
         ptx::mbar_wait(&ctl->tmem_full[as], (acc_it >> 1) & 1u);
         ptx::tc_fence_after();
         const int valid = min(kBlockN, p.c - nt * kBlockN);
+        // canonical summation order: 32-class partials -> one partial per 256-class tile -> row total over the
+        // tiles in class order.  The column-split mode stores the per-tile partials and its finish kernel adds
+        // them in the same order, so confidences are bit-identical however the work was cut.
+        float tile_sum = 0.f;
         for (int ch = 0; ch * 32 < valid; ++ch) {
           uint32_t raw[32];
           ptx::tmem_ld_32x32(tmem_base + lane_sel + as * kBlockN + ch * 32, raw);
           ptx::tmem_ld_wait(raw);
           const int nv = valid - ch * 32;
-          if (nv >= 32) exp_chunk<false, kMode>(raw, 32, a2, b2, sum, wsum);
-          else exp_chunk<true, kMode>(raw, nv, a2, b2, sum, wsum);
+          if (nv >= 32) exp_chunk<false, kMode>(raw, 32, a2, b2, tile_sum, wsum);
+          else exp_chunk<true, kMode>(raw, nv, a2, b2, tile_sum, wsum);
           if (kMode == 1) {
             const int rel = label - (nt * kBlockN + ch * 32);
             if (rel >= 0 && rel < 32) {
@@ -367,12 +371,11 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
             }
           }
         }
+        sum += tile_sum;
+        if (S > 1 && row_ok) p.part_sum[row * NT + nt] = tile_sum;
         release_acc(as);
       }
-      if (S > 1) {                                // column-split mode, second launch: partial sum only
-        if (row_ok) p.part_sum[row * S + split] = sum;
-        continue;
-      }
+      if (S > 1) continue;                        // column-split mode, second launch: per-tile partials are out
       // ---------------- per-row results
       if (kMode == 0) {
         const float conf = 1.0f / sum;
@@ -487,10 +490,10 @@ split_combine_max_kernel(const float* __restrict__ part_max, const int* __restri
   row_pred[row] = a;
 }
 
-// sum the per-range partial sums in a fixed order, emit (pred, conf, rowmax) and bin
+// add the per-tile partial sums in class order (the unsplit kernel's order), emit (pred, conf, rowmax) and bin
 __global__ void __launch_bounds__(256)
 split_finish_kernel(const float* __restrict__ part_sum, const float* __restrict__ row_max, const int* __restrict__ row_pred,
-                    long long n, int S, float scale, const int* __restrict__ split_exps, int* __restrict__ pred_out,
+                    long long n, int n_tiles, float scale, const int* __restrict__ split_exps, int* __restrict__ pred_out,
                     float* __restrict__ conf_out, float* __restrict__ rowmax_out, const long long* __restrict__ labels,
                     const __grid_constant__ ThrBlock thr, int n_thr, unsigned long long* __restrict__ table) {
   __shared__ BinCell cells[CCAL_MAX_THRESHOLDS + 1];
@@ -509,7 +512,7 @@ split_finish_kernel(const float* __restrict__ part_sum, const float* __restrict_
     int pred = 0;
     if (ok) {
       float sum = 0.f;
-      for (int s = 0; s < S; ++s) sum += part_sum[row * S + s];
+      for (int t = 0; t < n_tiles; ++t) sum += part_sum[row * n_tiles + t];      // same order as the unsplit kernel
       conf = 1.0f / sum;
       pred = row_pred[row];
       if (pred_out) pred_out[row] = pred;
@@ -634,12 +637,13 @@ static int launch_fused(int mode, const void* img, const void* txt, const void* 
   // ---- column-split orchestration: pass 1 per range -> combine -> pass 2 per range -> finish
   AsyncWorkspace workspace;
   const size_t per = ((size_t)n * S * 4 + 255) & ~(size_t)255, per_row = ((size_t)n * 4 + 255) & ~(size_t)255;
-  CCAL_CUDA_OK(workspace.alloc(3 * per + 2 * per_row, stream));
+  const size_t per_tiles = ((size_t)n * p.n_col_tiles * 4 + 255) & ~(size_t)255;
+  CCAL_CUDA_OK(workspace.alloc(2 * per + per_tiles + 2 * per_row, stream));
   float* part_max = (float*)workspace.ptr;
   int* part_arg = (int*)(workspace.ptr + per);
   float* part_sum = (float*)(workspace.ptr + 2 * per);
-  float* row_max = (float*)(workspace.ptr + 3 * per);
-  int* row_pred = (int*)(workspace.ptr + 3 * per + per_row);
+  float* row_max = (float*)(workspace.ptr + 2 * per + per_tiles);
+  int* row_pred = (int*)(workspace.ptr + 2 * per + per_tiles + per_row);
   ScoreParams q = p;
   q.pass_lo = q.pass_hi = 0;
   q.part_max = part_max; q.part_arg = part_arg;
@@ -651,7 +655,7 @@ static int launch_fused(int mode, const void* img, const void* txt, const void* 
   q.row_max_in = row_max; q.row_pred_in = row_pred; q.part_sum = part_sum;
   if ((rc = launch(q))) return rc;
   split_finish_kernel<<<rows_grid < 4 * sms_all ? rows_grid : 4 * sms_all, 256, 0, stream>>>(
-      part_sum, row_max, row_pred, (long long)n, S, p.scale, p.split_exps, p.pred_out, p.conf_out, p.rowmax_out, p.labels, thr,
+      part_sum, row_max, row_pred, (long long)n, p.n_col_tiles, p.scale, p.split_exps, p.pred_out, p.conf_out, p.rowmax_out, p.labels, thr,
       p.n_thr, p.table);
   note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
