@@ -198,10 +198,15 @@ radix_hist_level1(const float* __restrict__ keys, long long n, const __grid_cons
   __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const unsigned bits = __float_as_uint(keys[i]);
+    const unsigned bits = __float_as_uint(__ldcs(keys + i));
     const unsigned hi = bits >> 16;
-    for (int p = 0; p < n_prefix; ++p)
-      if (s_pref[p] == hi) atomicAdd(&hist[(size_t)p * 65536u + (bits & 0xFFFFu)], 1u);
+    int slot = -1;
+    for (int p = 0; p < n_prefix; ++p) slot = (s_pref[p] == hi) ? p : slot;
+    // saturated confidences (thousands of identical keys) would serialise on one address: aggregate equal keys per warp
+    const unsigned key = slot >= 0 ? ((unsigned)slot << 16) | (bits & 0xFFFFu) : 0xFFFFFFFFu;
+    const unsigned peers = __match_any_sync(__activemask(), key);
+    if (slot >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1)
+      atomicAdd(&hist[(size_t)slot * 65536u + (bits & 0xFFFFu)], (unsigned)__popc(peers));
   }
 }
 
