@@ -1,21 +1,27 @@
 // K2 / K5: fused scoring on tcgen05 + TMEM + TMA (sm_100a).
 //
-//   logits = s * img @ txt^T  is NEVER written to HBM.  For each 128-row image tile:
-//     pass 1: stream all text tiles (256 classes x 64 features per TMA box), accumulate
-//             128 x 256 fp32 tiles in TMEM, epilogue keeps the running row max / argmax;
+//   logits = s * img @ txt^T  is NEVER written to HBM.  For each image tile (256 rows per CTA pair, 128 per CTA):
+//     pass 1: stream all text tiles (256 classes x 64 features per step), accumulate 128 x 256 fp32 tiles per CTA
+//             in TMEM, epilogue keeps the running row max / first argmax;
 //     pass 2: stream the text tiles again, epilogue accumulates sum_j exp(cc[pred]*(l_j - l_max))
-//             -> confidence = 1 / sum, then bins (confidence, correct) into a shared-memory
-//             histogram (warp-aggregated atomics).
-//   The image tile (128 x D) stays RESIDENT in shared memory for both passes when D <= 512, so
-//   HBM reads every image feature exactly once; the text matrix is re-streamed from L2.
+//             -> confidence = 1 / sum, then bins (confidence, correct) into a shared-memory histogram
+//             (warp-aggregated atomics).
+//   The image tile (128 x D per CTA) stays RESIDENT in shared memory for both passes when D <= 640, so HBM reads
+//   every image feature exactly once; the text matrix is re-streamed from L2.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA
-// issuer (one lane), warps 2..5 = epilogue (each owns 32 TMEM lanes = 32 image rows).
-// Pipelines: A slabs (full/empty per 64-feature slab), B ring (full/empty per stage), two TMEM
-// accumulator stages (full/empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Variants of the one templated kernel (all parity-tested, all ~99.9 % tensor-pipe active under ncu):
+//   kCtas      1 = single CTAs (cta_group::1), 2 = CTA pairs (cta_group::2, each CTA loads half of every text tile)
+//   kResident  image tile resident (D <= 640) or both operands streamed through the ring (D up to 1024)
+//   kMode      0 = DAC scoring (ccal_score_fused), 1 = temperature-scaling loss/gradient (ccal_ts_loss_grad:
+//              pass 2 also accumulates sum exp*z and picks the label logit)
+//   kSplit     fp32 features as fp16 hi/lo pairs, 3 MMAs per K step (fp32-grade logits)
+//   column-split work units (runtime): few rows x many classes -> every row tile is cut into class ranges and the
+//              kernel runs once per pass with two tiny combine kernels between (small-batch latency mode).
 //
-// kMode 0 = DAC scoring (ccal_score_fused), kMode 1 = temperature-scaling loss/gradient
-// (ccal_ts_loss_grad: pass 2 also accumulates sum exp*z and picks the label logit).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (pair leader), warps 2..5 =
+// epilogue (each owns 32 TMEM lanes = 32 image rows).  Producer / issuer loops are warp-uniform with one
+// elect.sync lane issuing.  Pipelines: A slabs (full/empty per 64-feature slab), B ring (full/empty per stage),
+// two TMEM accumulator stages (full/empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "ccal_common.cuh"
 #include "sm100_ptx.cuh"
 
