@@ -390,5 +390,9 @@ def test_bad_arguments_fail_loudly(cuda_lib):
                            torch.zeros(8, 64, dtype=torch.bfloat16, device="cuda"))          # mixed operand dtypes
     with pytest.raises(ValueError):
         native.knn_l2(torch.zeros(4, 64, device="cuda"), torch.zeros(4, 64, device="cuda"), 99)
+    bad = DistanseAwareCalibration()
+    bad.class_confidence = np.array([1.0, -0.5, 1.0])
+    with pytest.raises(ValueError):
+        bad.predict(np.zeros((2, 3), np.float32))
     with pytest.raises(Exception):
         native.bin_stats(torch.zeros(4), torch.zeros(4, dtype=torch.int32), torch.zeros(4, dtype=torch.int64), [0.5])
