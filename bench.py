@@ -307,7 +307,8 @@ def main():
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        native.score_fused(img, txt_op, cc, LOGIT_SCALE, labels, thr, table, want_pred=False, want_conf=False)
+        # per-image (pred, conf) are written too (8 B/image), although only the bin table is needed for the metric
+        native.score_fused(img, txt_op, cc, LOGIT_SCALE, labels, thr, table, want_pred=True, want_conf=True)
         if record:
             e1.record()
             kern_events.append((e0, e1))
