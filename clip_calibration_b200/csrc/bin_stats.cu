@@ -122,21 +122,33 @@ bin_stats_fast_kernel(const float* __restrict__ conf, const PredT* __restrict__ 
                          reinterpret_cast<uintptr_t>(gt)) & 15) == 0;
   long long done = 0;
   if (aligned) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-      const float4 x = __ldcs(reinterpret_cast<const float4*>(conf) + i);
-      long long p[4];
+    struct Quad { float4 x; long long p[4]; longlong2 g0, g1; };
+    auto load = [&](long long i) {
+      Quad q;
+      q.x = __ldcs(reinterpret_cast<const float4*>(conf) + i);
       if (sizeof(PredT) == 4) {
-        const int4 q = __ldcs(reinterpret_cast<const int4*>(pred) + i);
-        p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
+        const int4 v = __ldcs(reinterpret_cast<const int4*>(pred) + i);
+        q.p[0] = v.x; q.p[1] = v.y; q.p[2] = v.z; q.p[3] = v.w;
       } else {
-        const longlong2 q0 = __ldcs(reinterpret_cast<const longlong2*>(pred) + 2 * i);
-        const longlong2 q1 = __ldcs(reinterpret_cast<const longlong2*>(pred) + 2 * i + 1);
-        p[0] = q0.x; p[1] = q0.y; p[2] = q1.x; p[3] = q1.y;
+        const longlong2 v0 = __ldcs(reinterpret_cast<const longlong2*>(pred) + 2 * i);
+        const longlong2 v1 = __ldcs(reinterpret_cast<const longlong2*>(pred) + 2 * i + 1);
+        q.p[0] = v0.x; q.p[1] = v0.y; q.p[2] = v1.x; q.p[3] = v1.y;
       }
-      const longlong2 g0 = __ldcs(reinterpret_cast<const longlong2*>(gt) + 2 * i);
-      const longlong2 g1 = __ldcs(reinterpret_cast<const longlong2*>(gt) + 2 * i + 1);
-      add(x.x, p[0], g0.x); add(x.y, p[1], g0.y); add(x.z, p[2], g1.x); add(x.w, p[3], g1.y);
+      q.g0 = __ldcs(reinterpret_cast<const longlong2*>(gt) + 2 * i);
+      q.g1 = __ldcs(reinterpret_cast<const longlong2*>(gt) + 2 * i + 1);
+      return q;
+    };
+    auto consume = [&](const Quad& q) {
+      add(q.x.x, q.p[0], q.g0.x); add(q.x.y, q.p[1], q.g0.y); add(q.x.z, q.p[2], q.g1.x); add(q.x.w, q.p[3], q.g1.y);
+    };
+    // two independent 4-image groups per iteration: 128 B of loads in flight per thread
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n4; i += 2 * stride) {
+      const Quad a = load(i), b = load(i + stride);
+      consume(a);
+      consume(b);
     }
+    if (i < n4) consume(load(i));
     done = n4 * 4;
   }
   for (long long i = done + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
