@@ -74,11 +74,10 @@ bin_stats_kernel(const ConfT* __restrict__ conf, const PredT* __restrict__ pred,
 constexpr int kFastCells = 16;
 constexpr int kFastWarps = kBinThreads / 32;
 
-struct __align__(16) LaneCell {
-  unsigned int count;
-  unsigned int correct;
-  unsigned long long sum_fx;
-};
+// per lane and bin: {count (low 16 bits) | correct (high 16 bits)} and the 64-bit fixed-point confidence sum, in two
+// arrays so that an update is one 4-byte and one 8-byte conflict-free read-modify-write.  A thread sees fewer than
+// 65,536 images per launch (n < 2^32 over >= 592 x 256 threads), so the packed 16-bit counters cannot overflow.
+struct LaneCounts { unsigned int count_correct; };
 
 // kUniform: the thresholds are within half a bin of (i+1)/n_thr (every ECE/MCE table), so the bin is
 // floor(x * n_thr) corrected by at most one step against the exact thresholds: 2 compares instead of n_thr.
@@ -88,14 +87,16 @@ bin_stats_fast_kernel(const float* __restrict__ conf, const PredT* __restrict__ 
                       const long long* __restrict__ gt, long long n,
                       const __grid_constant__ Thr32 thr, int n_thr, unsigned long long* __restrict__ table) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  LaneCell* cells = reinterpret_cast<LaneCell*>(smem_raw);           // [kFastWarps][n_cells][32]
-  __shared__ float s_thr[kFastCells];
   const int n_cells = n_thr + 1;
+  unsigned long long* sums = reinterpret_cast<unsigned long long*>(smem_raw);          // [kFastWarps][n_cells][32]
+  unsigned int* counts = reinterpret_cast<unsigned int*>(sums + kFastWarps * n_cells * 32);   // same shape
+  __shared__ float s_thr[kFastCells];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < kFastWarps * n_cells * 32; i += blockDim.x) cells[i] = LaneCell{0u, 0u, 0ull};
+  for (int i = threadIdx.x; i < kFastWarps * n_cells * 32; i += blockDim.x) { sums[i] = 0ull; counts[i] = 0u; }
   if (threadIdx.x < kFastCells) s_thr[threadIdx.x] = threadIdx.x < n_thr ? thr.t[threadIdx.x] : 0.f;
   __syncthreads();
-  LaneCell* mine = cells + (size_t)warp * n_cells * 32 + lane;
+  unsigned long long* my_sum = sums + (size_t)warp * n_cells * 32 + lane;
+  unsigned int* my_cnt = counts + (size_t)warp * n_cells * 32 + lane;
 
   const float fn = (float)n_thr;
   auto add = [&](float x, long long p, long long g) {
@@ -109,11 +110,8 @@ bin_stats_fast_kernel(const float* __restrict__ conf, const PredT* __restrict__ 
     } else {
       for (int j = 0; j < n_thr; ++j) b += (x >= s_thr[j]) ? 1 : 0;
     }
-    LaneCell c = mine[b * 32];
-    c.count += 1u;
-    c.correct += (p == g) ? 1u : 0u;
-    c.sum_fx += conf_to_fx(x);
-    mine[b * 32] = c;
+    my_cnt[b * 32] += (p == g) ? 0x10001u : 1u;
+    my_sum[b * 32] += conf_to_fx(x);
   };
 
   const long long n4 = n / 4;
@@ -158,8 +156,9 @@ bin_stats_fast_kernel(const float* __restrict__ conf, const PredT* __restrict__ 
   for (int cell = warp; cell < n_cells; cell += kFastWarps) {
     unsigned long long cnt = 0, cor = 0, sm = 0;
     for (int w = 0; w < kFastWarps; ++w) {
-      const LaneCell c = cells[((size_t)w * n_cells + cell) * 32 + lane];
-      cnt += c.count; cor += c.correct; sm += c.sum_fx;
+      const unsigned int cc = counts[((size_t)w * n_cells + cell) * 32 + lane];
+      cnt += cc & 0xFFFFu; cor += cc >> 16;
+      sm += sums[((size_t)w * n_cells + cell) * 32 + lane];
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -262,8 +261,11 @@ extern "C" int ccal_bin_stats(const void* conf, int conf_f64, const void* pred, 
     // float keys: compare against ceil_f32(threshold) (equivalent to the double comparison)
     Thr32 tf;
     for (int i = 0; i < CCAL_MAX_THRESHOLDS; ++i) tf.t[i] = i < n_thr ? ceil_to_f32(thresholds_host[i]) : 0.0f;
-    const size_t fsmem = sizeof(LaneCell) * kFastWarps * n_cells * 32;
+    const size_t fsmem = (size_t)12 * kFastWarps * n_cells * 32;
+    // >= 592 CTAs whenever there is that much work keeps every thread below 65,536 images (packed 16-bit counters)
     const int fgrid = grid_for((n + 3) / 4, kBinThreads, 4);
+    CCAL_REQUIRE((n + (long long)fgrid * kBinThreads - 1) / ((long long)fgrid * kBinThreads) < 65536,
+                 "ccal_bin_stats: too many images per thread for the packed counters (n=%lld on %d CTAs)", (long long)n, fgrid);
     bool uniform = n_thr >= 1;
     for (int i = 0; i < n_thr; ++i)
       uniform = uniform && fabs(thresholds_host[i] - (double)(i + 1) / n_thr) < 0.25 / n_thr;
