@@ -44,6 +44,12 @@ __device__ __forceinline__ float group_sum(float s) {
   return s;
 }
 
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 enum RowOp { kScaleInPlace = 0, kConfidence = 1, kSoftmaxInPlace = 2, kArgmaxOnly = 3 };
 
 template <int GROUP, int OP>
@@ -188,12 +194,16 @@ logits_rows_reg_kernel(float* __restrict__ logits, const float* __restrict__ cla
       const int j = lane + 32 * u;
       v[u] = (j < c4) ? __ldcs(x4 + j) : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
     }
+    // a lane visits its classes in increasing index order, so a strict > keeps the first maximum; the full
+    // (value, index) tie rule is only needed across lanes
     MaxIdx m{-CUDART_INF_F, 0x7fffffff};
 #pragma unroll
     for (int u = 0; u < NV4; ++u) {
       const int j = 4 * (lane + 32 * u);
-      m = better(m, MaxIdx{v[u].x, j}); m = better(m, MaxIdx{v[u].y, j + 1});
-      m = better(m, MaxIdx{v[u].z, j + 2}); m = better(m, MaxIdx{v[u].w, j + 3});
+      if (v[u].x > m.v) { m.v = v[u].x; m.i = j; }
+      if (v[u].y > m.v) { m.v = v[u].y; m.i = j + 1; }
+      if (v[u].z > m.v) { m.v = v[u].z; m.i = j + 2; }
+      if (v[u].w > m.v) { m.v = v[u].w; m.i = j + 3; }
     }
     m = group_argmax<32>(m);
     const int pred = m.i;
@@ -219,9 +229,12 @@ logits_rows_reg_kernel(float* __restrict__ logits, const float* __restrict__ cla
       continue;
     }
     const float mcc = __fmul_rn(m.v, cc);
+    const float cc2 = cc * 1.4426950408889634f, mcc2 = mcc * 1.4426950408889634f;
     auto ex = [&](float t) {
-      const float a = __fsub_rn(__fmul_rn(t, cc), mcc);
-      return OP == kConfidence ? __expf(a) : expf(a);
+      // returned probabilities: the reference's fp32 arithmetic (scale, shift, accurate exp); confidence only:
+      // one FMA + ex2 per class (relative error ~2e-6, far inside the 1e-4 budget)
+      if (OP == kConfidence) return exp2f_approx(fmaf(t, cc2, -mcc2));
+      return expf(__fsub_rn(__fmul_rn(t, cc), mcc));
     };
     float s = 0.f;
 #pragma unroll
