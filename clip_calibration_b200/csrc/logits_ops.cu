@@ -14,6 +14,12 @@
 
 namespace ccal {
 
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct MaxIdx {
   float v;
   int i;
@@ -44,12 +50,6 @@ __device__ __forceinline__ float group_sum(float s) {
   return s;
 }
 
-__device__ __forceinline__ float exp2f_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 enum RowOp { kScaleInPlace = 0, kConfidence = 1, kSoftmaxInPlace = 2, kArgmaxOnly = 3 };
 
 template <int GROUP, int OP>
@@ -74,19 +74,24 @@ logits_rows_kernel(float* __restrict__ logits, const float* __restrict__ class_c
     float* x = logits + (live ? row : 0) * (long long)c;
     float4* x4 = reinterpret_cast<float4*>(x);
 
-    // ---- sweep 1: first argmax
+    // ---- sweep 1: first argmax (a thread visits its classes in increasing index order: strict > suffices locally)
     MaxIdx m{-CUDART_INF_F, 0x7fffffff};
     if (live) {
       if (vec) {
 #pragma unroll 4
         for (int j = t; j < c4; j += GROUP) {
           const float4 v = x4[j];
-          m = better(m, MaxIdx{v.x, 4 * j}); m = better(m, MaxIdx{v.y, 4 * j + 1});
-          m = better(m, MaxIdx{v.z, 4 * j + 2}); m = better(m, MaxIdx{v.w, 4 * j + 3});
+          if (v.x > m.v) { m.v = v.x; m.i = 4 * j; }
+          if (v.y > m.v) { m.v = v.y; m.i = 4 * j + 1; }
+          if (v.z > m.v) { m.v = v.z; m.i = 4 * j + 2; }
+          if (v.w > m.v) { m.v = v.w; m.i = 4 * j + 3; }
         }
       } else {
 #pragma unroll 4
-        for (int j = t; j < c; j += GROUP) m = better(m, MaxIdx{x[j], j});
+        for (int j = t; j < c; j += GROUP) {
+          const float v = x[j];
+          if (v > m.v) { m.v = v; m.i = j; }
+        }
       }
     }
     m = group_argmax<GROUP>(m);
@@ -128,11 +133,12 @@ logits_rows_kernel(float* __restrict__ logits, const float* __restrict__ class_c
 
     // ---- sweep 2: sum of exp of the DAC-scaled, max-shifted row (scipy softmax arithmetic)
     const float mcc = __fmul_rn(m.v, cc);
-    // probabilities that are RETURNED use the accurate expf; the confidence-only variant sums
-    // thousands of terms and uses the MUFU-based __expf (relative error ~2e-6)
+    // probabilities that are RETURNED use the reference's fp32 arithmetic and the accurate expf; the
+    // confidence-only variant uses one FMA + ex2 per class (relative error ~2e-6)
+    const float cc2 = cc * 1.4426950408889634f, mcc2 = mcc * 1.4426950408889634f;
     auto ex = [&](float v) {
-      const float a = __fsub_rn(__fmul_rn(v, cc), mcc);
-      return OP == kConfidence ? __expf(a) : expf(a);
+      if (OP == kConfidence) return exp2f_approx(fmaf(v, cc2, -mcc2));
+      return expf(__fsub_rn(__fmul_rn(v, cc), mcc));
     };
     float s = 0.f;
     if (live) {
