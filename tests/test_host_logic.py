@@ -153,3 +153,36 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["config"]["workload"].startswith("open-vocabulary") and d["metric"].startswith("calibrated images/sec")
+
+
+def test_tempscaling_surface_without_dassl(tmp_path):
+    """Reference surface that must import and work without dassl / a GPU: ScaleLearner (param name, init, exp),
+    CustomCLIPCalibration.forward contract, checkpoint file names and the dassl-format scalar checkpoint."""
+    import torch
+    from clip_calibration_b200.trainers.calibration import tempscaling as ts
+    learner = ts.ScaleLearner(None, torch.float32)
+    assert list(learner.state_dict()) == ["logit_scale"] and abs(float(learner.logit_scale) - 4.6052) < 1e-6
+    assert abs(float(learner().detach()) - np.exp(4.6052)) < 1e-3
+
+    class Base(torch.nn.Module):
+        dtype = torch.float32
+
+        def forward(self, image):
+            f = torch.nn.functional.normalize(image, dim=-1)
+            t = torch.nn.functional.normalize(torch.eye(4, 8), dim=-1)
+            return f @ t.t(), f, t
+
+    model = ts.CustomCLIPCalibration(None, Base())
+    logits, img_f, txt_f = model(torch.randn(3, 8))
+    assert logits.shape == (3, 4) and torch.allclose(logits, model.scale_learner() * img_f @ txt_f.t())
+    assert ts.calibrated_checkpoint_name(None) == "model-calibrated-best.pth.tar"
+    assert ts.calibrated_checkpoint_name(20) == "model-calibrated.pth.tar-20"
+    path = ts.save_logit_scale(str(tmp_path), 4.25, 20)
+    assert path.endswith(os.path.join("tempscaling", "model-calibrated.pth.tar-20"))
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ckpt) >= {"state_dict", "epoch", "optimizer", "scheduler", "val_result"} and list(ckpt["state_dict"]) == ["logit_scale"]
+    assert abs(ts.load_logit_scale(str(tmp_path), 20) - 4.25) < 1e-6
+    with pytest.raises(FileNotFoundError):
+        ts.load_logit_scale(str(tmp_path), 99)
+    with pytest.raises(ImportError):
+        ts.TempScaling()                       # the trainer itself needs dassl
