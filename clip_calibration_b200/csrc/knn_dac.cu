@@ -19,6 +19,7 @@ constexpr int kChunk = 16;       // feature chunk
 constexpr int kPad = 68;         // padded row length of the transposed chunks
 constexpr int kRowsPerWarp = 8;
 constexpr int kMaxList = CCAL_MAX_K + 1;
+constexpr int kRedoSmallRows = 256;
 
 struct TopList {                 // lane l holds the l-th smallest (d, i) seen so far
   float d;
@@ -54,7 +55,8 @@ knn_l2_kernel(const float* __restrict__ ref, const float* __restrict__ query, lo
   const int ld_row = tid >> 2, ld_col = (tid & 3) * 4;
   const int cap = min((long long)(k + (drop_first ? 1 : 0)), nr);   // list length actually used
   const long long nq = qlist ? (long long)*qcount : nq_all;
-  for (long long q0 = (long long)blockIdx.x * kTile; q0 < nq; q0 += (long long)gridDim.x * kTile) {
+  const long long q_first = qlist ? kRedoSmallRows : 0;      // list mode: the first rows belong to knn_redo_rows_kernel
+  for (long long q0 = q_first + (long long)blockIdx.x * kTile; q0 < nq; q0 += (long long)gridDim.x * kTile) {
   // global row of this thread's staged query row (list mode gathers)
   const long long ld_q = (q0 + ld_row < nq) ? (qlist ? (long long)qlist[q0 + ld_row] : q0 + ld_row) : -1;
 
@@ -145,6 +147,66 @@ knn_l2_kernel(const float* __restrict__ ref, const float* __restrict__ query, lo
   }
 }
 
+
+// Redo kernel for a HANDFUL of query rows (the rows the tensor-core filter could not prove): one CTA per listed row,
+// each warp scans a strided subset of the reference rows with lane-strided exact fp32 distances and keeps its own
+// sorted top list (one entry per lane); warp 0 merges the 8 lists.  A single row costs microseconds here, where the
+// 64-query tiled scan above would spend a whole CTA-pass over all reference rows on it.
+constexpr int kRedoSmallMax = kRedoSmallRows;   // rows [0, 256) of the list go through this kernel, the rest through the tiled scan
+
+__global__ void __launch_bounds__(256)
+knn_redo_rows_kernel(const float* __restrict__ ref, const float* __restrict__ query, long long nr, int d, int k,
+                     int drop_first, float* __restrict__ dist_out, int* __restrict__ idx_out,
+                     const int* __restrict__ qlist, const int* __restrict__ qcount) {
+  __shared__ float s_d[8][kMaxList];
+  __shared__ int s_i[8][kMaxList];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cap = (int)min((long long)(k + (drop_first ? 1 : 0)), nr);
+  const int count = min(*qcount, kRedoSmallMax);
+  for (int e = blockIdx.x; e < count; e += gridDim.x) {
+    const long long q = qlist[e];
+    const float4* qv = reinterpret_cast<const float4*>(query + q * d);
+    TopList mine{CUDART_INF_F, 0x7fffffff};
+    for (long long r = warp; r < nr; r += 8) {
+      const float4* rv = reinterpret_cast<const float4*>(ref + r * d);
+      float acc = 0.f;
+      for (int j = lane; j < d / 4; j += 32) {
+        const float4 a = qv[j], b = rv[j];
+        float df = b.x - a.x; acc = fmaf(df, df, acc);
+        df = b.y - a.y; acc = fmaf(df, df, acc);
+        df = b.z - a.z; acc = fmaf(df, df, acc);
+        df = b.w - a.w; acc = fmaf(df, df, acc);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      const float dist = sqrtf(acc);
+      const float kth = __shfl_sync(0xffffffffu, mine.d, cap - 1);
+      const int kth_i = __shfl_sync(0xffffffffu, mine.i, cap - 1);
+      if (dist < kth || (dist == kth && (int)r < kth_i)) list_insert(mine, dist, (int)r, cap, lane);   // warp-uniform
+    }
+    if (lane < cap) { s_d[warp][lane] = mine.d; s_i[warp][lane] = mine.i; }
+    __syncthreads();
+    if (warp == 0) {
+      TopList all{CUDART_INF_F, 0x7fffffff};
+      for (int w = 0; w < 8; ++w)
+        for (int t = 0; t < cap; ++t) {
+          const float cd = s_d[w][t];
+          const int ci = s_i[w][t];
+          const float kth = __shfl_sync(0xffffffffu, all.d, cap - 1);
+          const int kth_i = __shfl_sync(0xffffffffu, all.i, cap - 1);
+          if (ci != 0x7fffffff && (cd < kth || (cd == kth && ci < kth_i))) list_insert(all, cd, ci, cap, lane);
+        }
+      const int slot = lane - (drop_first ? 1 : 0);
+      if (slot >= 0 && slot < k) {
+        const bool have = lane < cap;
+        if (dist_out) dist_out[q * k + slot] = have ? all.d : CUDART_INF_F;
+        if (idx_out) idx_out[q * k + slot] = have ? all.i : -1;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // numpy's float32 add.reduce over a short contiguous vector (pairwise_sum for n < 128)
 __device__ __forceinline__ float numpy_sum_f32(const float* a, int n) {
   if (n < 8) {
@@ -178,9 +240,13 @@ __global__ void dac_map_kernel(const float* __restrict__ dist_zs, const float* _
 
 int launch_knn_exact(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k, int drop_first,
                      float* dist_out, int32_t* idx_out, const int* qlist, const int* qcount, cudaStream_t stream) {
+  if (qlist != nullptr) {
+    knn_redo_rows_kernel<<<64, 256, 0, stream>>>(ref, query, (long long)nr, d, k, drop_first, dist_out, idx_out, qlist, qcount);
+    note_launch();
+  }
   long long grid = (nq + kTile - 1) / kTile;
   const long long cap = (long long)num_sms() * 4;
-  if (qlist != nullptr && grid > cap) grid = cap;     // list mode: usually (almost) nothing to do
+  if (qlist != nullptr && grid > cap) grid = cap;     // list mode: rows beyond the first 256 (normally none)
   if (grid > 2147483647ll) grid = 2147483647ll;
   knn_l2_kernel<<<(int)grid, 256, 0, stream>>>(ref, query, (long long)nr, (long long)nq, d, k, drop_first,
                                                dist_out, idx_out, qlist, qcount);
