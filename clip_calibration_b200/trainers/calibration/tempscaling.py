@@ -115,6 +115,37 @@ def fit_logit_scale(image_features, text_features, labels, epochs: int = 20, lr:
     return t
 
 
+def solve_logit_scale(image_features, text_features, labels, lo: float = 0.0, hi: float = math.log(1000.0),
+                      tol: float = 1e-6, max_iter: int = 60, operand_dtype=None) -> float:
+    """The minimiser of the temperature-scaling objective itself (additive; no optimiser hyper-parameters):
+    L(t) = CE(exp(t) * img @ txt.T, y) is convex in s = exp(t), so dL/dt has a single sign change; it is
+    bracketed on [lo, hi] and located by bisection with safeguarded secant steps, each evaluation being one
+    fused pass over the WHOLE cached validation set (ccal_ts_loss_grad).  Returns log-scale t*; if the
+    gradient does not change sign on the bracket the better end point is returned."""
+    img, txt, y = _operands(image_features, text_features, labels, operand_dtype)
+
+    def grad(t: float) -> float:
+        return float(native.ts_loss_grad(img, txt, y, t).cpu()[1])
+
+    g_lo, g_hi = grad(lo), grad(hi)
+    if g_lo >= 0.0:
+        return lo
+    if g_hi <= 0.0:
+        return hi
+    for _ in range(max_iter):
+        t = hi - g_hi * (hi - lo) / (g_hi - g_lo)                  # secant (regula falsi) proposal
+        if not (lo + 0.05 * (hi - lo) < t < hi - 0.05 * (hi - lo)):
+            t = 0.5 * (lo + hi)                                    # safeguard: fall back to bisection
+        g = grad(t)
+        if g > 0.0:
+            hi, g_hi = t, g
+        else:
+            lo, g_lo = t, g
+        if hi - lo < tol or abs(g) < 1e-9:
+            break
+    return 0.5 * (lo + hi)
+
+
 # ----------------------------------------------------------------------------------------
 # checkpoint format of the scalar (dassl save_checkpoint layout, reference :260-300, :305-327)
 # ----------------------------------------------------------------------------------------

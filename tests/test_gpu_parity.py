@@ -305,6 +305,12 @@ def test_fit_logit_scale_reduces_loss_and_checkpoint_roundtrip(cuda_lib, tmp_pat
     t = tempscaling.fit_logit_scale(case.img, case.txt_tuned, case.labels, epochs=5)
     l1, g1 = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t)
     assert l1 < l0
+    # the objective's own minimiser: gradient ~ 0 there and no SGD trajectory beats it
+    t_star = tempscaling.solve_logit_scale(case.img, case.txt_tuned, case.labels)
+    l_star, g_star = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t_star)
+    assert abs(g_star) < 1e-4 and l_star <= l1 + 1e-9
+    for dt in (-0.05, 0.05):
+        assert orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t_star + dt)[0] > l_star
     tempscaling.save_logit_scale(str(tmp_path), t, 5)
     assert abs(tempscaling.load_logit_scale(str(tmp_path), 5) - t) < 1e-6
     learner = tempscaling.ScaleLearner(None, torch.float32)
