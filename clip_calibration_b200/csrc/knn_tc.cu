@@ -1,10 +1,11 @@
 // K1 (tensor-core path): k nearest reference rows by exact fp32 Euclidean distance, found with a
 // tcgen05 GEMM as a FILTER and verified exactly.
 //
-//   1. split_rows_kernel : x -> hi = bf16(x), lo = bf16(x - hi), and 0.5*|x|^2 (fp32).
-//   2. knn_tc_kernel     : S = q.r from three bf16 MMAs (hi.hi + hi.lo + lo.hi, fp32 accumulate in
-//                          TMEM; the dropped lo.lo term is < 2^-18 |q||r|), epilogue keeps per query
-//                          the KP best candidates by the score  S - 0.5|r|^2  (= -d^2/2 + const).
+//   1. split_rows_kernel : x -> hi = bf16(x), lo = bf16(x - hi), 0.5*|x|^2 (fp32), plus one extra feature
+//                          column (1 for queries, -|r|^2/2 for references) that folds the norm term into the GEMM.
+//   2. knn_tc_kernel     : score = q.r - |r|^2/2 (= -d^2/2 + const) from three bf16 MMAs (hi.hi + hi.lo + lo.hi,
+//                          fp32 accumulate in TMEM; the dropped lo.lo term is < 2^-18 |q||r|); the epilogue
+//                          keeps per query the KP best candidates (branch-free prefilter, sorted insert on hits).
 //   3. knn_verify_kernel : recomputes ||r - q||_2 for the KP candidates in fp32 with the
 //                          reference's own formula, sorts them (distance, index) and PROVES that no
 //                          discarded reference row can beat the k-th: every discarded row has
@@ -41,12 +42,17 @@ struct __align__(16) KnnCtl {
 };
 
 // ---------------------------------------------------------------------------------------- 1
+// Output rows are d + 64 wide: the extra 64-feature block holds ONE non-zero column that folds the -|r|^2/2
+// term of the score into the GEMM itself: queries get 1.0 there, reference rows get -|r|^2/2 (as a hi/lo pair),
+// so the accumulator is directly  q.r - |r|^2/2  and the filter's epilogue is a bare compare per element.
 __global__ void __launch_bounds__(256)
 split_rows_kernel(const float* __restrict__ x, long long rows, int d, __nv_bfloat16* __restrict__ hi,
-                  __nv_bfloat16* __restrict__ lo, float* __restrict__ half_norm2, unsigned int* __restrict__ max_norm2_bits) {
+                  __nv_bfloat16* __restrict__ lo, float* __restrict__ half_norm2, unsigned int* __restrict__ max_norm2_bits,
+                  int is_reference) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;
   if (row >= rows) return;
+  const int dp = d + kTcBlockK;
   const float4* src = reinterpret_cast<const float4*>(x + row * d);
   float acc = 0.f;
   for (int j = lane; j < d / 4; j += 32) {
@@ -59,11 +65,20 @@ split_rows_kernel(const float* __restrict__ x, long long rows, int d, __nv_bfloa
       l[u] = __float2bfloat16_rn(f[u] - __bfloat162float(h[u]));
       acc = fmaf(f[u], f[u], acc);
     }
-    *reinterpret_cast<uint2*>(hi + row * d + 4 * j) = *reinterpret_cast<uint2*>(h);
-    *reinterpret_cast<uint2*>(lo + row * d + 4 * j) = *reinterpret_cast<uint2*>(l);
+    *reinterpret_cast<uint2*>(hi + row * dp + 4 * j) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + row * dp + 4 * j) = *reinterpret_cast<uint2*>(l);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  // extra block: column d carries the fold term, columns d+1 .. d+63 are zero
+  const float extra = is_reference ? -0.5f * acc : 1.0f;
+  const __nv_bfloat16 eh = __float2bfloat16_rn(extra);
+  const __nv_bfloat16 el = __float2bfloat16_rn(extra - __bfloat162float(eh));
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  for (int j = lane; j < kTcBlockK; j += 32) {
+    hi[row * dp + d + j] = (j == 0) ? eh : zero;
+    lo[row * dp + d + j] = (j == 0) ? el : zero;
+  }
   if (lane == 0) {
     half_norm2[row] = 0.5f * acc;
     if (max_norm2_bits) atomicMax(max_norm2_bits, __float_as_uint(acc));   // non-negative floats order like uints
@@ -206,11 +221,18 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
           ptx::tmem_ld_32x32(tmem_base + lane_sel + as * kTcBlockN + ch * 32, raw);
           ptx::tmem_ld_wait(raw);
           const int col0 = nt * kTcBlockN + ch * 32;
+          const int nv = (int)min(32ll, p.nr - col0);              // valid columns in this chunk (>= 1)
+          // branch-free prefilter: which of the 32 scores beat the current worst kept candidate?
+          const float worst = ts[KP - 1];
+          uint32_t hits = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < p.nr) {
-              const float t = __uint_as_float(raw[j]) - __ldg(p.r_half_norm2 + col0 + j);
-              if (t > ts[KP - 1]) {
+          for (int j = 0; j < 32; ++j) hits |= (uint32_t)(__uint_as_float(raw[j]) > worst) << j;
+          if (nv < 32) hits &= (1u << nv) - 1u;
+          if (hits) {                                              // rare once the lists have warmed up
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float t = __uint_as_float(raw[j]);
+              if (((hits >> j) & 1u) && t > ts[KP - 1]) {
                 // sorted insert, descending; equal scores keep the earlier (lower) index ahead
                 float ct = t;
                 int ci = col0 + j;
@@ -331,20 +353,21 @@ static int run_tc(const float* ref, const float* query, int64_t nr, int64_t nq, 
                   float* dist_out, int32_t* idx_out, const __nv_bfloat16* rhi, const __nv_bfloat16* rlo,
                   const float* rhn, const unsigned int* rmax, __nv_bfloat16* qhi, __nv_bfloat16* qlo, float* qhn, int* cand, float* cut,
                   int* redo_list, int* redo_count, cudaStream_t stream) {
-  split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(query, nq, d, qhi, qlo, qhn, nullptr);
+  const int dp = d + kTcBlockK;                      // operand rows carry one extra 64-feature block (see split_rows_kernel)
+  split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(query, nq, d, qhi, qlo, qhn, nullptr, 0);
   note_launch();
   // CTA pairs when every pair gets at least one 256-row tile on most SMs; single CTAs for small query sets
   const int sms = num_sms();
   const int ctas = (nq >= (int64_t)kTcBlockM * 2 * (sms / 4)) ? 2 : 1;
   CUtensorMap mqh, mql, mrh, mrl;
   int rc;
-  if ((rc = make_map(&mqh, qhi, nq, d, kTcBlockM, CCAL_BF16))) return rc;
-  if ((rc = make_map(&mql, qlo, nq, d, kTcBlockM, CCAL_BF16))) return rc;
-  if ((rc = make_map(&mrh, rhi, nr, d, kTcBlockN / ctas, CCAL_BF16))) return rc;
-  if ((rc = make_map(&mrl, rlo, nr, d, kTcBlockN / ctas, CCAL_BF16))) return rc;
+  if ((rc = make_map(&mqh, qhi, nq, dp, kTcBlockM, CCAL_BF16))) return rc;
+  if ((rc = make_map(&mql, qlo, nq, dp, kTcBlockM, CCAL_BF16))) return rc;
+  if ((rc = make_map(&mrh, rhi, nr, dp, kTcBlockN / ctas, CCAL_BF16))) return rc;
+  if ((rc = make_map(&mrl, rlo, nr, dp, kTcBlockN / ctas, CCAL_BF16))) return rc;
   KnnTcParams p{};
   p.nq = nq; p.nr = nr;
-  p.kblocks = d / kTcBlockK;
+  p.kblocks = dp / kTcBlockK;
   p.n_col_tiles = (int)((nr + kTcBlockN - 1) / kTcBlockN);
   const int tile_rows = kTcBlockM * ctas;
   p.n_row_tiles = (int)((nq + tile_rows - 1) / tile_rows);
@@ -397,8 +420,9 @@ int knn_l2_tensor(const float* ref, const float* query, int64_t nr, int64_t nq, 
   const size_t bf = sizeof(__nv_bfloat16);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  const size_t o_rhi = take((size_t)nr * d * bf), o_rlo = take((size_t)nr * d * bf), o_rhn = take((size_t)nr * 4);
-  const size_t o_qhi = take((size_t)chunk * d * bf), o_qlo = take((size_t)chunk * d * bf), o_qhn = take((size_t)chunk * 4);
+  const size_t dp = (size_t)d + kTcBlockK;
+  const size_t o_rhi = take((size_t)nr * dp * bf), o_rlo = take((size_t)nr * dp * bf), o_rhn = take((size_t)nr * 4);
+  const size_t o_qhi = take((size_t)chunk * dp * bf), o_qlo = take((size_t)chunk * dp * bf), o_qhn = take((size_t)chunk * 4);
   const size_t o_cand = take((size_t)chunk * KP * 4), o_cut = take((size_t)chunk * 4);
   const size_t o_list = take((size_t)chunk * 4), o_cnt = take(256), o_rmax = take(256);
   AsyncWorkspace workspace;
@@ -409,7 +433,7 @@ int knn_l2_tensor(const float* ref, const float* query, int64_t nr, int64_t nq, 
   float* rhn = (float*)(ws + o_rhn);
   unsigned int* rmax = (unsigned int*)(ws + o_rmax);
   cudaMemsetAsync(rmax, 0, sizeof(unsigned int), stream);
-  split_rows_kernel<<<(unsigned)((nr + 7) / 8), 256, 0, stream>>>(ref, nr, d, rhi, rlo, rhn, rmax);
+  split_rows_kernel<<<(unsigned)((nr + 7) / 8), 256, 0, stream>>>(ref, nr, d, rhi, rlo, rhn, rmax, 1);
   note_launch();
   int rc = CCAL_OK;
   for (int64_t q0 = 0; q0 < nq && rc == CCAL_OK; q0 += chunk) {
