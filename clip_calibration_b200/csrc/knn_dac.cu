@@ -11,6 +11,7 @@
 #include "ccal_common.cuh"
 
 #include <math_constants.h>
+#include <algorithm>
 
 namespace ccal {
 
@@ -19,7 +20,7 @@ constexpr int kChunk = 16;       // feature chunk
 constexpr int kPad = 68;         // padded row length of the transposed chunks
 constexpr int kRowsPerWarp = 8;
 constexpr int kMaxList = CCAL_MAX_K + 1;
-constexpr int kRedoSmallRows = 256;
+constexpr int kRedoSmallRows = 96;
 
 struct TopList {                 // lane l holds the l-th smallest (d, i) seen so far
   float d;
@@ -148,62 +149,107 @@ knn_l2_kernel(const float* __restrict__ ref, const float* __restrict__ query, lo
 }
 
 
-// Redo kernel for a HANDFUL of query rows (the rows the tensor-core filter could not prove): one CTA per listed row,
-// each warp scans a strided subset of the reference rows with lane-strided exact fp32 distances and keeps its own
-// sorted top list (one entry per lane); warp 0 merges the 8 lists.  A single row costs microseconds here, where the
-// 64-query tiled scan above would spend a whole CTA-pass over all reference rows on it.
-constexpr int kRedoSmallMax = kRedoSmallRows;   // rows [0, 256) of the list go through this kernel, the rest through the tiled scan
+// Redo path for a HANDFUL of query rows (the rows the tensor-core filter could not prove).  The reference rows are
+// spread over ALL SMs (thread t of the grid owns reference rows t, t + T, ...), so one unproven row costs microseconds
+// instead of a serial scan by one SM.  Every lane accumulates the exact fp32 distance to its own reference row over
+// the features in ascending order - the same order as the tiled scan, so both paths return identical floats.  Each
+// CTA writes its sorted partial list; knn_redo_merge_kernel combines the partials with the (distance, index) order.
+constexpr int kRedoSmallMax = kRedoSmallRows;   // rows [0, kRedoSmallRows) of the list take this path, the rest the tiled scan
+constexpr int kRedoThreads = 128;
 
-__global__ void __launch_bounds__(256)
-knn_redo_rows_kernel(const float* __restrict__ ref, const float* __restrict__ query, long long nr, int d, int k,
-                     int drop_first, float* __restrict__ dist_out, int* __restrict__ idx_out,
-                     const int* __restrict__ qlist, const int* __restrict__ qcount) {
-  __shared__ float s_d[8][kMaxList];
-  __shared__ int s_i[8][kMaxList];
+// all lanes call; lanes offer (cd, ci) (ci < 0: nothing); the list keeps the `cap` smallest by (d, i)
+__device__ __forceinline__ void list_offer(TopList& list, float cd, int ci, int cap, int lane) {
+  float kth = __shfl_sync(0xffffffffu, list.d, cap - 1);
+  int kth_i = __shfl_sync(0xffffffffu, list.i, cap - 1);
+  unsigned pending = __ballot_sync(0xffffffffu, ci >= 0 && (cd < kth || (cd == kth && ci < kth_i)));
+  while (pending) {
+    const int src = __ffs(pending) - 1;
+    pending &= pending - 1;
+    const float sd = __shfl_sync(0xffffffffu, cd, src);
+    const int si = __shfl_sync(0xffffffffu, ci, src);
+    if (sd < kth || (sd == kth && si < kth_i)) {                      // warp-uniform
+      list_insert(list, sd, si, cap, lane);
+      kth = __shfl_sync(0xffffffffu, list.d, cap - 1);
+      kth_i = __shfl_sync(0xffffffffu, list.i, cap - 1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRedoThreads)
+knn_redo_scan_kernel(const float* __restrict__ ref, const float* __restrict__ query, long long nr, int d, int cap,
+                     const int* __restrict__ qlist, const int* __restrict__ qcount,
+                     float* __restrict__ part_d, int* __restrict__ part_i) {
+  extern __shared__ __align__(16) float s_q[];          // the query row
+  __shared__ float s_d[kRedoThreads / 32][kMaxList];
+  __shared__ int s_i[kRedoThreads / 32][kMaxList];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cap = (int)min((long long)(k + (drop_first ? 1 : 0)), nr);
   const int count = min(*qcount, kRedoSmallMax);
-  for (int e = blockIdx.x; e < count; e += gridDim.x) {
+  const long long stride = (long long)gridDim.x * kRedoThreads;
+  for (int e = 0; e < count; ++e) {
     const long long q = qlist[e];
-    const float4* qv = reinterpret_cast<const float4*>(query + q * d);
+    for (int j = threadIdx.x; j < d; j += kRedoThreads) s_q[j] = query[q * d + j];
+    __syncthreads();
     TopList mine{CUDART_INF_F, 0x7fffffff};
-    for (long long r = warp; r < nr; r += 8) {
-      const float4* rv = reinterpret_cast<const float4*>(ref + r * d);
-      float acc = 0.f;
-      for (int j = lane; j < d / 4; j += 32) {
-        const float4 a = qv[j], b = rv[j];
-        float df = b.x - a.x; acc = fmaf(df, df, acc);
-        df = b.y - a.y; acc = fmaf(df, df, acc);
-        df = b.z - a.z; acc = fmaf(df, df, acc);
-        df = b.w - a.w; acc = fmaf(df, df, acc);
+    for (long long base = (long long)blockIdx.x * kRedoThreads + warp * 32; base < nr; base += stride) {
+      const long long r = base + lane;
+      float dist = CUDART_INF_F;
+      if (r < nr) {
+        const float4* rv = reinterpret_cast<const float4*>(ref + r * d);
+        const float4* qv = reinterpret_cast<const float4*>(s_q);
+        float acc = 0.f;
+#pragma unroll 16
+        for (int j = 0; j < d / 4; ++j) {
+          const float4 a = qv[j], b = __ldg(rv + j);
+          float df = b.x - a.x; acc = fmaf(df, df, acc);
+          df = b.y - a.y; acc = fmaf(df, df, acc);
+          df = b.z - a.z; acc = fmaf(df, df, acc);
+          df = b.w - a.w; acc = fmaf(df, df, acc);
+        }
+        dist = sqrtf(acc);
       }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      const float dist = sqrtf(acc);
-      const float kth = __shfl_sync(0xffffffffu, mine.d, cap - 1);
-      const int kth_i = __shfl_sync(0xffffffffu, mine.i, cap - 1);
-      if (dist < kth || (dist == kth && (int)r < kth_i)) list_insert(mine, dist, (int)r, cap, lane);   // warp-uniform
+      list_offer(mine, dist, r < nr ? (int)r : -1, cap, lane);
     }
     if (lane < cap) { s_d[warp][lane] = mine.d; s_i[warp][lane] = mine.i; }
     __syncthreads();
     if (warp == 0) {
       TopList all{CUDART_INF_F, 0x7fffffff};
-      for (int w = 0; w < 8; ++w)
-        for (int t = 0; t < cap; ++t) {
-          const float cd = s_d[w][t];
-          const int ci = s_i[w][t];
-          const float kth = __shfl_sync(0xffffffffu, all.d, cap - 1);
-          const int kth_i = __shfl_sync(0xffffffffu, all.i, cap - 1);
-          if (ci != 0x7fffffff && (cd < kth || (cd == kth && ci < kth_i))) list_insert(all, cd, ci, cap, lane);
-        }
-      const int slot = lane - (drop_first ? 1 : 0);
-      if (slot >= 0 && slot < k) {
-        const bool have = lane < cap;
-        if (dist_out) dist_out[q * k + slot] = have ? all.d : CUDART_INF_F;
-        if (idx_out) idx_out[q * k + slot] = have ? all.i : -1;
+      for (int w = 0; w < kRedoThreads / 32; ++w) {
+        const float cd = lane < cap ? s_d[w][lane] : CUDART_INF_F;
+        const int ci = lane < cap ? s_i[w][lane] : -1;
+        list_offer(all, cd, ci == 0x7fffffff ? -1 : ci, cap, lane);
+      }
+      if (lane < cap) {
+        const long long o = ((long long)e * gridDim.x + blockIdx.x) * cap + lane;
+        part_d[o] = all.d;
+        part_i[o] = all.i;
       }
     }
     __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(32)
+knn_redo_merge_kernel(const float* __restrict__ part_d, const int* __restrict__ part_i, int parts, int cap, int k,
+                      int drop_first, float* __restrict__ dist_out, int* __restrict__ idx_out,
+                      const int* __restrict__ qlist, const int* __restrict__ qcount) {
+  const int lane = threadIdx.x;
+  const int count = min(*qcount, kRedoSmallMax);
+  for (int e = blockIdx.x; e < count; e += gridDim.x) {
+    const long long q = qlist[e];
+    TopList all{CUDART_INF_F, 0x7fffffff};
+    const long long total = (long long)parts * cap;
+    for (long long t0 = 0; t0 < total; t0 += 32) {
+      const long long t = t0 + lane;
+      const float cd = t < total ? part_d[(long long)e * total + t] : CUDART_INF_F;
+      const int ci = t < total ? part_i[(long long)e * total + t] : -1;
+      list_offer(all, cd, ci == 0x7fffffff ? -1 : ci, cap, lane);
+    }
+    const int slot = lane - (drop_first ? 1 : 0);
+    if (slot >= 0 && slot < k) {
+      const bool have = lane < cap;
+      if (dist_out) dist_out[q * k + slot] = have ? all.d : CUDART_INF_F;
+      if (idx_out) idx_out[q * k + slot] = have ? all.i : -1;
+    }
   }
 }
 
@@ -240,8 +286,19 @@ __global__ void dac_map_kernel(const float* __restrict__ dist_zs, const float* _
 
 int launch_knn_exact(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k, int drop_first,
                      float* dist_out, int32_t* idx_out, const int* qlist, const int* qcount, cudaStream_t stream) {
+  AsyncWorkspace ws;
   if (qlist != nullptr) {
-    knn_redo_rows_kernel<<<64, 256, 0, stream>>>(ref, query, (long long)nr, d, k, drop_first, dist_out, idx_out, qlist, qcount);
+    const int cap = (int)std::min<int64_t>(k + (drop_first ? 1 : 0), nr);
+    const int parts = (int)std::min<int64_t>(num_sms(), (nr + kRedoThreads - 1) / kRedoThreads);
+    const size_t cells = (size_t)kRedoSmallMax * parts * cap;
+    CCAL_CUDA_OK(ws.alloc(cells * (sizeof(float) + sizeof(int)), stream));
+    float* part_d = reinterpret_cast<float*>(ws.ptr);
+    int* part_i = reinterpret_cast<int*>(ws.ptr + cells * sizeof(float));
+    knn_redo_scan_kernel<<<parts, kRedoThreads, (size_t)d * sizeof(float), stream>>>(ref, query, (long long)nr, d, cap, qlist,
+                                                                                   qcount, part_d, part_i);
+    note_launch();
+    knn_redo_merge_kernel<<<kRedoSmallMax, 32, 0, stream>>>(part_d, part_i, parts, cap, k, drop_first, dist_out, idx_out,
+                                                            qlist, qcount);
     note_launch();
   }
   long long grid = (nq + kTile - 1) / kTile;
