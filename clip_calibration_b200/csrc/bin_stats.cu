@@ -228,6 +228,45 @@ static int grid_for(long long n, int threads, int per_sm) {
   return (int)(want < cap ? want : cap);
 }
 
+// ----------------------------------------------------------------------------------------
+// per-class confusion counts {tp, fp, fn} behind macro-F1 (evaluators/vl_evaluator.py:74-79)
+// ----------------------------------------------------------------------------------------
+constexpr int kClassSmemMax = 2048;        // classes privatised in shared memory (3 x u32 each)
+
+template <typename PredT, bool kSmem>
+__global__ void __launch_bounds__(kBinThreads)
+class_counts_kernel(const PredT* __restrict__ pred, const long long* __restrict__ gt, long long n, int c,
+                    unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned int s_cnt[];   // [c][3] when kSmem
+  if (kSmem) {
+    for (int j = threadIdx.x; j < 3 * c; j += blockDim.x) s_cnt[j] = 0;
+    __syncthreads();
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long p = (long long)pred[i], g = gt[i];
+    const bool p_ok = p >= 0 && p < c, g_ok = g >= 0 && g < c;
+    if (kSmem) {
+      if (p == g) { if (g_ok) atomicAdd(&s_cnt[3 * g], 1u); }
+      else {
+        if (p_ok) atomicAdd(&s_cnt[3 * p + 1], 1u);
+        if (g_ok) atomicAdd(&s_cnt[3 * g + 2], 1u);
+      }
+    } else {
+      if (p == g) { if (g_ok) atomicAdd(&counts[3 * g], 1ull); }
+      else {
+        if (p_ok) atomicAdd(&counts[3 * p + 1], 1ull);
+        if (g_ok) atomicAdd(&counts[3 * g + 2], 1ull);
+      }
+    }
+  }
+  if (kSmem) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < 3 * c; j += blockDim.x)
+      if (s_cnt[j]) atomicAdd(&counts[j], (unsigned long long)s_cnt[j]);
+  }
+}
+
 }  // namespace ccal
 
 using namespace ccal;
@@ -318,6 +357,29 @@ extern "C" int ccal_radix_hist(const float* keys, int64_t n, int level, const ui
     radix_hist_level1<<<grid, kBinThreads, 0, stream>>>(keys, (long long)n, pf, n_prefix, hist);
     note_launch();
   }
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}
+
+extern "C" int ccal_class_counts(const void* pred, int pred_i64, const int64_t* gt, int64_t n, int c,
+                                 unsigned long long* counts, ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE(n >= 0 && n < (1ll << 32), "ccal_class_counts: n out of range");
+  CCAL_REQUIRE(c >= 1, "ccal_class_counts: c must be positive (got %d)", c);
+  CCAL_REQUIRE(counts != nullptr, "ccal_class_counts: counts is NULL");
+  if (n == 0) return CCAL_OK;
+  CCAL_REQUIRE(pred && gt, "ccal_class_counts: NULL input");
+  const long long* g = reinterpret_cast<const long long*>(gt);
+  const int grid = grid_for(n, kBinThreads, 8);
+  const size_t smem = (size_t)3 * c * sizeof(unsigned int);
+  if (c <= kClassSmemMax) {
+    if (pred_i64) class_counts_kernel<long long, true><<<grid, kBinThreads, smem, stream>>>((const long long*)pred, g, n, c, counts);
+    else class_counts_kernel<int, true><<<grid, kBinThreads, smem, stream>>>((const int*)pred, g, n, c, counts);
+  } else {
+    if (pred_i64) class_counts_kernel<long long, false><<<grid, kBinThreads, 0, stream>>>((const long long*)pred, g, n, c, counts);
+    else class_counts_kernel<int, false><<<grid, kBinThreads, 0, stream>>>((const int*)pred, g, n, c, counts);
+  }
+  note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
 }

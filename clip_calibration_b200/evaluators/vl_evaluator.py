@@ -1,10 +1,10 @@
 """The metric half of the reference's evaluators/vl_evaluator.py (`VLClassification.evaluate`,
-reference :59-116): accuracy, error, mean confidence, ECE, MCE, ACE (and PIECE when a proximity
-vector is given), as percentages in the reference's result keys.
+reference :59-116): accuracy, error, macro-F1, mean confidence, ECE, MCE, ACE (and PIECE when a
+proximity vector is given), as percentages in the reference's result keys.
 
-In scope: argmax / confidence gather / accuracy / mean confidence (:65-84) and the calibration
-metrics (:86-92).  Out of scope: macro-F1 (sklearn, host-side) and the reliability plot
-(matplotlib) - the per-bin table needed to draw it is returned under "bin_table".
+In scope: argmax / confidence gather / accuracy / mean confidence (:65-84), macro-F1 from per-class
+{tp, fp, fn} counted on the device (:74-79) and the calibration metrics (:86-92).  The reliability plot
+(:118-137, matplotlib) is tools/plot.py; the per-bin table it draws is returned under "bin_table".
 """
 from __future__ import annotations
 
@@ -19,13 +19,14 @@ from ..tools import metrics
 
 
 def evaluate_pred_conf(preds, confs, labels, ece_bins: int = 10, piece_bins: int = 10, proximity=None,
-                       group=None) -> "OrderedDict[str, float]":
+                       group=None, n_classes=None) -> "OrderedDict[str, float]":
     """Metrics from per-image (pred, conf, label); numpy or CUDA tensors."""
     table = metrics.bin_stats(confs, preds, labels, ece_bins, group)
     results = OrderedDict()
     acc = 100.0 * tm.accuracy(table)
     results["accuracy"] = acc
     results["error_rate"] = 100.0 - acc
+    results["macro_f1"] = 100.0 * metrics.macro_f1(preds, labels, n_classes, group)
     results["confidence"] = tm.mean_confidence(table)
     results["ece"] = 100.0 * float(tm.ece_from_table(table))
     results["mce"] = 100.0 * float(tm.mce_from_table(table))
@@ -42,4 +43,4 @@ def evaluate(probs, labels, text_proximity=None, ece_bins: int = 10, piece_bins:
     p = probs if isinstance(probs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(probs))
     p = p.to(device="cuda", dtype=torch.float32).contiguous()
     pred, conf = native.row_argmax(p)              # preds = argmax(probs), confs = probs[i, preds_i]
-    return evaluate_pred_conf(pred, conf, labels, ece_bins, piece_bins, text_proximity)
+    return evaluate_pred_conf(pred, conf, labels, ece_bins, piece_bins, text_proximity, n_classes=p.shape[1])

@@ -241,6 +241,48 @@ def row_argmax(values: torch.Tensor):
 
 
 # --------------------------------------------------------------------------------------
+# f-4  density-ratio calibration (2-D Gaussian KDE + row recalibration)
+# --------------------------------------------------------------------------------------
+def kde2_pdf(data_x: torch.Tensor, data_y: torch.Tensor, query_x: torch.Tensor, query_y: torch.Tensor,
+             bw_x: float, bw_y: float) -> torch.Tensor:
+    """Product-Gaussian kernel density of the float64 points (data_x, data_y) [M] at (query_x, query_y) [N]."""
+    lib = _lib.load()
+    data_x = _need_cuda("data_x", data_x, torch.float64, 1)
+    data_y = _need_cuda("data_y", data_y, torch.float64, 1)
+    query_x = _need_cuda("query_x", query_x, torch.float64, 1)
+    query_y = _need_cuda("query_y", query_y, torch.float64, 1)
+    if data_x.shape != data_y.shape or query_x.shape != query_y.shape:
+        raise ValueError("kde2_pdf: x / y length mismatch")
+    out = torch.empty(query_x.shape[0], dtype=torch.float64, device=query_x.device)
+    with torch.cuda.device(query_x.device):
+        rc = lib.ccal_kde2_pdf(_ptr(data_x), _ptr(data_y), data_x.shape[0], _ptr(query_x), _ptr(query_y),
+                               query_x.shape[0], float(bw_x), float(bw_y), _ptr(out), _stream())
+    _lib.check(rc, "ccal_kde2_pdf")
+    return out
+
+
+def density_ratio_apply(probs: torch.Tensor, pdf_true: torch.Tensor, pdf_false: torch.Tensor, ratio: float):
+    """(probs_out float64 [N, C], conf_cal float64 [N], pred int32 [N]) - see ccal_density_ratio_apply."""
+    lib = _lib.load()
+    probs = _need_cuda("probs", probs, (torch.float32, torch.float64), 2)
+    n, c = probs.shape
+    pdf_true = _need_cuda("pdf_true", pdf_true, torch.float64, 1)
+    pdf_false = _need_cuda("pdf_false", pdf_false, torch.float64, 1)
+    if pdf_true.shape[0] != n or pdf_false.shape[0] != n:
+        raise ValueError("density_ratio_apply: one density value per row is required")
+    out = torch.empty((n, c), dtype=torch.float64, device=probs.device)
+    cal = torch.empty(n, dtype=torch.float64, device=probs.device)
+    pred = torch.empty(n, dtype=torch.int32, device=probs.device)
+    f32 = probs.dtype == torch.float32
+    with torch.cuda.device(probs.device):
+        rc = lib.ccal_density_ratio_apply(_ptr(probs) if f32 else None, None if f32 else _ptr(probs), n, c,
+                                          _ptr(pdf_true), _ptr(pdf_false), float(ratio), _ptr(out), _ptr(cal),
+                                          _ptr(pred), _stream())
+    _lib.check(rc, "ccal_density_ratio_apply")
+    return out, cal, pred
+
+
+# --------------------------------------------------------------------------------------
 # K3  bin statistics and exact order statistics
 # --------------------------------------------------------------------------------------
 def bin_stats(conf: torch.Tensor, pred: torch.Tensor, gt: torch.Tensor, thresholds: Sequence[float],
@@ -272,6 +314,26 @@ def bin_stats(conf: torch.Tensor, pred: torch.Tensor, gt: torch.Tensor, threshol
                                 _ptr(key2), thr2, n_thr2, _ptr(table), _stream())
     _lib.check(rc, "ccal_bin_stats")
     return table
+
+
+def class_counts(pred: torch.Tensor, gt: torch.Tensor, n_classes: int,
+                 counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Accumulate per-class {tp, fp, fn} into an int64 [n_classes, 3] table (created zeroed if not given)."""
+    lib = _lib.load()
+    pred = _need_cuda("pred", pred, (torch.int32, torch.int64), 1)
+    gt = _need_cuda("gt", gt, torch.int64, 1)
+    if pred.shape != gt.shape:
+        raise ValueError("class_counts: pred / gt length mismatch")
+    if counts is None:
+        counts = torch.zeros((int(n_classes), 3), dtype=torch.int64, device=pred.device)
+    elif not (counts.is_cuda and counts.is_contiguous() and counts.dtype == torch.int64
+              and tuple(counts.shape) == (int(n_classes), 3)):
+        raise ValueError("class_counts: counts must be a contiguous int64 CUDA tensor [n_classes, 3]")
+    with torch.cuda.device(pred.device):
+        rc = lib.ccal_class_counts(_ptr(pred), int(pred.dtype == torch.int64), _ptr(gt), pred.shape[0],
+                                   int(n_classes), _ptr(counts), _stream())
+    _lib.check(rc, "ccal_class_counts")
+    return counts
 
 
 def radix_hist(keys: torch.Tensor, level: int, prefixes: Optional[Sequence[int]] = None,

@@ -151,3 +151,22 @@ def edges_from_order_stats(x_lo, x_hi, gamma) -> np.ndarray:
     edges = np.asarray(lerp_like_numpy(x_lo, x_hi, gamma), dtype=np.float64)
     keep = np.ediff1d(edges, to_begin=np.inf) > 1e-8
     return edges[keep]
+
+
+def macro_f1_from_counts(counts) -> float:
+    """sklearn.metrics.f1_score(labels, preds, average="macro", labels=np.unique(labels)) (the call of
+    evaluators/vl_evaluator.py:74-79) from a per-class {tp, fp, fn} table: F1 of every class that occurs among
+    the true labels (tp + fn > 0), 0 where a class is never predicted correctly, averaged with equal weights."""
+    counts = np.asarray(counts).astype(np.float64).reshape(-1, 3)
+    tp, fp, fn = counts[:, 0], counts[:, 1], counts[:, 2]
+    present = (tp + fn) > 0
+    if not present.any():
+        return 0.0
+    tp, fp, fn = tp[present], fp[present], fn[present]
+    pred_sum, true_sum = tp + fp, tp + fn
+    with np.errstate(invalid="ignore", divide="ignore"):
+        precision = np.where(pred_sum > 0, tp / pred_sum, 0.0)
+        recall = tp / true_sum
+        denom = precision + recall
+        f1 = np.where(denom > 0, 2.0 * precision * recall / denom, 0.0)
+    return float(np.mean(f1))

@@ -8,7 +8,7 @@ quantile bins - runs in CUDA (ccal_bin_stats / ccal_radix_hist); the host only c
 place.  There is no CPU fallback: without an sm_100 GPU these functions raise.
 
 Additive entry points (not in the reference): bin_stats, ece_from_table, mce_from_table,
-calibration_summary, and the `group=` argument that all-reduces tables across ranks.
+calibration_summary, class_counts / macro_f1 (the evaluator's sklearn call), and the `group=` argument that all-reduces tables across ranks.
 """
 from __future__ import annotations
 
@@ -112,6 +112,25 @@ def PIECE(conf, knndist, pred, gt, dist_bin_num=10, conf_bin_num=10, knn_strateg
     else:
         table = native.bin_stats(_conf_dev(conf), _pred_dev(pred), _dev(gt, torch.int64), thr, key2, thr2)
     return tm.sum_of_gaps(native.table_to_numpy(_allreduce(table, group)))
+
+
+def class_counts(pred, gt, n_classes=None, group=None) -> np.ndarray:
+    """[n_classes, 3] int64 table {tp, fp, fn} per class, counted on the device (ccal_class_counts)."""
+    p, g = _pred_dev(pred), _dev(gt, torch.int64)
+    if n_classes is None:
+        n_classes = int(max(int(p.max()), int(g.max())) + 1) if p.numel() else 1
+        if group is not None:
+            c = torch.tensor([n_classes], dtype=torch.int64, device=p.device)
+            torch.distributed.all_reduce(c, op=torch.distributed.ReduceOp.MAX, group=group)
+            n_classes = int(c.item())
+    counts = native.class_counts(p, g, n_classes)
+    return _allreduce(counts, group).cpu().numpy()
+
+
+def macro_f1(pred, gt, n_classes=None, group=None) -> float:
+    """`f1_score(labels, preds, average="macro", labels=np.unique(labels))` as a fraction
+    (evaluators/vl_evaluator.py:74-79 multiplies by 100)."""
+    return tm.macro_f1_from_counts(class_counts(pred, gt, n_classes, group))
 
 
 def calibration_summary(table) -> dict:

@@ -1,9 +1,11 @@
 """Drop-in for the DAC + softmax branch of the reference's trainers/calibration/vl_calibrator.py
 (`VLCalibration.__init__ / fit / predict / build_dac_calibrator`, reference :30-109, :155-180).
 
-In scope: DAC (dac_flag) followed by softmax.  The bin-based / density-ratio base calibrators
-(reference :112-150; netcal / statsmodels CPU statistics) are out of scope: requesting one
-raises NotImplementedError instead of silently skipping it.
+In scope: DAC (dac_flag) followed by softmax, and the `scaling_based` base calibrator with
+`procal_flag` = DensityRatioCalibration (reference :116-119, :95-96; CUDA KDE, see
+density_ratio_calibration.py).  The `bin_based` base calibrators (reference :121-148; netcal
+HistogramBinning / IsotonicRegression and sklearn isotonic regression, CPU statistics libraries)
+are out of scope: requesting one raises NotImplementedError instead of silently skipping it.
 
 `predict(logits, proximity)` keeps the reference contract and returns probabilities [N, C].
 `predict_confidence` / `predict_from_features` are the additive routes that return only
@@ -15,6 +17,7 @@ import numpy as np
 import torch
 
 from ... import native
+from .density_ratio_calibration import DensityRatioCalibration
 from .distanse_aware_calibration import DistanseAwareCalibration
 
 
@@ -22,12 +25,12 @@ class VLCalibration():
 
     def __init__(self, cfg, base_calibration_mode=None, base_bin_calibrator_name=None, dac_flag=False,
                  procal_flag=False, val_dict=None, text_feature_dict=None):
-        if base_calibration_mode is not None:
+        if base_calibration_mode not in (None, "scaling_based"):
             raise NotImplementedError(
-                "base calibrators (scaling_based / bin_based; netcal + statsmodels in the reference) are outside "
+                "bin_based base calibrators (netcal / sklearn isotonic regression in the reference) are outside "
                 "the accelerated path; use the reference's VLCalibration for them")
         self.cfg = cfg
-        self.base_calibration_mode = None
+        self.base_calibration_mode = base_calibration_mode
         self.base_bin_calibrator_name = base_bin_calibrator_name
         self.dac_flag = dac_flag
         self.procal_flag = procal_flag
@@ -45,6 +48,23 @@ class VLCalibration():
         self.base_calibrator = None
         if self.dac_flag:
             self.dac_calibrator = self.build_dac_calibrator(self.text_feature_dict, self.k_dac)
+        if self.base_calibration_mode is not None:
+            self.base_calibrator = self.build_base_calibrator(self.base_bin_calibrator_name, self.val_image_proximity)
+
+    def build_base_calibrator(self, base_bin_calibrator_name, val_image_proximity):
+        """reference :112-150, `scaling_based` branch: the density-ratio calibrator is fitted on the validation
+        (calibration) set - softmax of the un-scaled validation logits (:59-60), their argmax, labels, proximity."""
+        if not (self.base_calibration_mode == "scaling_based" and self.procal_flag):
+            return None                             # the reference builds nothing in this case either
+        val_logits = self.val_dict["val_logits"]
+        x = val_logits.detach() if isinstance(val_logits, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(val_logits))
+        val_probs = x.to(device="cuda", dtype=torch.float32, copy=True).contiguous()
+        val_preds, _ = native.dac_softmax_logits_(val_probs, None)
+        labels = self.val_dict["val_labels"]
+        labels = labels.cpu().numpy() if isinstance(labels, torch.Tensor) else np.asarray(labels)
+        base_calibrator = DensityRatioCalibration()
+        base_calibrator.fit(val_probs, val_preds.cpu().numpy(), labels, val_image_proximity)
+        return base_calibrator
 
     def build_dac_calibrator(self, text_feature_dict, k_dac):
         dac_calibrator = DistanseAwareCalibration()
@@ -65,6 +85,9 @@ class VLCalibration():
         work = x.to(device="cuda", dtype=torch.float32, copy=True).contiguous()
         cc = self.dac_calibrator._cc() if self.dac_calibrator is not None else None
         native.dac_softmax_logits_(work, cc)
+        if self.base_calibrator is not None:          # scaling_based + proximity: float64 [N, C] like the reference
+            prox = test_proximity if isinstance(test_proximity, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(test_proximity))
+            work, _, _ = self.base_calibrator.predict_device(work, prox.cuda())
         return work.cpu().numpy() if as_numpy else work
 
     # ------------------------------------------------------------------ additive

@@ -165,6 +165,29 @@ CCAL_API int ccal_bin_stats(const void* conf, int conf_f64, const void* pred, in
 CCAL_API int ccal_radix_hist(const float* keys, int64_t n, int level, const uint32_t* prefixes_host,
                     int n_prefix, uint32_t* hist, ccal_stream_t stream);
 
+/* ---- per-class confusion counts (macro-F1, evaluators/vl_evaluator.py:74-79) ---------------
+ * counts[cls][3] += {tp: pred == gt == cls, fp: pred == cls != gt, fn: gt == cls != pred}; uint64, accumulating
+ * (caller zeroes), so per-rank tables can be all-reduced.  Labels / predictions outside [0, c) are ignored.
+ */
+CCAL_API int ccal_class_counts(const void* pred, int pred_i64, const int64_t* gt, int64_t n, int c,
+                      unsigned long long* counts, ccal_stream_t stream);
+
+/* ---- density-ratio (proximity-informed) calibration --------------------------------------
+ * Reference: trainers/calibration/density_ratio_calibration.py, DensityRatioCalibration.
+ * ccal_kde2_pdf = `sm.nonparametric.KDEMultivariate(data=[conf, proximity], var_type='cc').pdf(points)`
+ * (:66, :70, :104-105): pdf_out[q] = 1/(m 2 pi bw_x bw_y) * sum_i exp(-(x_i-qx)^2/(2 bw_x^2) - (y_i-qy)^2/(2 bw_y^2)),
+ * float64 in and out (device pointers), valid down to the float64 underflow limit.
+ * ccal_density_ratio_apply = the rest of .predict (:108-117): conf_cal = t / max(t + f*ratio, 1e-10); in every row
+ * the first-argmax class gets conf_cal and the other classes are rescaled to sum to 1 - conf_cal.  probs is fp32
+ * or fp64 (exactly one pointer non-NULL); probs_out is float64 [n,c]; conf_cal_out / pred_out may be NULL.
+ */
+CCAL_API int ccal_kde2_pdf(const double* data_x, const double* data_y, int64_t m, const double* query_x,
+                  const double* query_y, int64_t n, double bw_x, double bw_y, double* pdf_out,
+                  ccal_stream_t stream);
+CCAL_API int ccal_density_ratio_apply(const float* probs_f32, const double* probs_f64, int64_t n, int c,
+                             const double* pdf_true, const double* pdf_false, double false_true_ratio,
+                             double* probs_out, double* conf_cal_out, int32_t* pred_out, ccal_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,9 @@ Pinned: dac_fit, dac_predict, ece, mce, adaptive_ece, piece, knn_dists (against 
 imported reference functions) and softmax / argmax / confidence (against scipy+numpy as the
 reference calls them).  Parity UNPINNED: the TempScaling *trajectory* (dassl optimiser
 semantics are not in the reference tree); ts_loss_and_grad is pinned to torch autograd only.
+density_ratio_fit / density_ratio_predict: the reference's own arithmetic is pinned by running the real
+DensityRatioCalibration class over KDEMultivariateCC; the KDE itself restates statsmodels (absent here,
+unpinned in the reference's requirements.txt) -> that part is parity UNPINNED, cross-checked against sklearn.
 """
 from __future__ import annotations
 
@@ -265,3 +268,71 @@ def knn_dists(ref_rows, queries, k: int, drop_self: bool = False) -> np.ndarray:
         top, _ = torch.topk(d, k=kk, largest=False)
         out.append(top[1:].numpy() if drop_self else top.numpy())
     return np.array(out)
+
+
+# --------------------------------------------------------------------------------------
+# f-4  density-ratio (proximity-informed) calibration
+# --------------------------------------------------------------------------------------
+class KDEMultivariateCC:
+    """Restatement of `statsmodels.api.nonparametric.KDEMultivariate(data=[dep, indep], var_type='cc',
+    bw='normal_reference')` as the reference calls it (trainers/calibration/density_ratio_calibration.py:66,
+    :70) and of its `.pdf(data_predict)` (:104-105).
+
+    statsmodels is an UNPINNED third-party dependency (reference requirements.txt:7, no version) and is NOT
+    installed in the build container, so this follows its published algorithm (statsmodels 0.14,
+    nonparametric/_kernel_base.py `GenericKDE._normal_reference`, `gpke`; kernels.py `gaussian`):
+        bw_j   = 1.06 * std_j(ddof=0) * nobs ** (-1 / (4 + k_vars))
+        pdf(x) = 1/nobs * sum_i prod_j [ exp(-(X_ij - x_j)^2 / (2 bw_j^2)) / sqrt(2 pi) ] / prod_j bw_j
+    all in float64.  PARITY UNPINNED against statsmodels itself; cross-checked against
+    sklearn.neighbors.KernelDensity on bandwidth-scaled data in oracle/make_golden.py."""
+
+    def __init__(self, data, var_type="cc", bw="normal_reference"):
+        assert var_type == "cc" and bw == "normal_reference"
+        dat = np.asarray([np.asarray(v, dtype=np.float64) for v in data])     # [k_vars, nobs]
+        self.k_vars = dat.shape[0]
+        self.data = dat.T.reshape(-1, self.k_vars)                             # _adjust_shape -> [nobs, k_vars]
+        self.nobs = self.data.shape[0]
+        self.bw = 1.06 * np.std(self.data, axis=0) * self.nobs ** (-1.0 / (4 + self.k_vars))
+
+    def pdf(self, data_predict):
+        pts = np.asarray(data_predict, dtype=np.float64).reshape(-1, self.k_vars)
+        out = np.empty(len(pts), np.float64)
+        for i, x in enumerate(pts):
+            kval = (1.0 / np.sqrt(2 * np.pi)) * np.exp(-(self.data - x) ** 2 / (self.bw ** 2 * 2.0))
+            out[i] = (kval.prod(axis=1) / np.prod(self.bw)).sum(axis=0) / self.nobs
+        return out
+
+
+def density_ratio_fit(probs, preds, true, proximity):
+    """trainers/calibration/density_ratio_calibration.py:35-72 (DensityRatioCalibration.fit): KDE of
+    (confidence, proximity) over the correctly classified and over the misclassified validation samples,
+    and the false/true count ratio."""
+    probs = np.asarray(probs)
+    assert np.all(probs >= 0) and np.all(probs <= 1)
+    confs = np.max(probs, axis=-1)
+    correct = np.asarray(preds) == np.asarray(true)
+    proximity = np.asarray(proximity)
+    dens_true = KDEMultivariateCC([confs[correct], proximity[correct]])
+    dens_false = KDEMultivariateCC([confs[~correct], proximity[~correct]])
+    ratio = (~correct).sum() / correct.sum()
+    return dens_true, dens_false, ratio
+
+
+def density_ratio_predict(state, probs, proximities):
+    """trainers/calibration/density_ratio_calibration.py:78-117 (DensityRatioCalibration.predict): Bayes
+    posterior of `correct` given (confidence, proximity); the predicted class gets that value, the other
+    classes are rescaled to sum to one minus it.  Returns (probs_out [N, C] float64, conf_calibrated [N])."""
+    dens_true, dens_false, ratio = state
+    probs = np.asarray(probs)
+    preds = np.argmax(probs, axis=-1)
+    confs = np.max(probs, axis=-1)
+    data = np.array([confs, proximities]).T
+    t = dens_true.pdf(data)
+    f = dens_false.pdf(data)
+    cal = t / np.maximum(t + f * ratio, 1e-10)
+    mask = np.ones(probs.shape, dtype=bool)
+    mask[np.arange(probs.shape[0]), preds] = False
+    rest = probs * mask
+    out = rest * ((1 - cal) / rest.sum(axis=-1))[:, np.newaxis]
+    out[np.arange(probs.shape[0]), preds] = cal
+    return out, cal

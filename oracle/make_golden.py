@@ -9,6 +9,8 @@ Reference entry points executed unmodified:
       (.cuda() patched to identity: the container has no GPU)
   tools/metrics.py   ECE, MCE, AdaptiveECE, PIECE
   trainers/calibration/proximity.py   get_knn_dists, get_val_image_knn_dists (.to('cuda') patched)
+  trainers/calibration/density_ratio_calibration.py  DensityRatioCalibration.fit/.predict (statsmodels stubbed
+      with the oracle's restatement of KDEMultivariate - the package is not installed)
 and the glue the reference performs inline: `(s*img)@txt.T` in fp32 torch
 (trainers/classification/zsclip.py:97-102), scipy.special.softmax(axis=-1)
 (trainers/calibration/vl_calibrator.py:91), argmax + gather (evaluators/vl_evaluator.py:68,:83).
@@ -167,11 +169,63 @@ def proximity_and_piece():
     print("proximity_piece: piece10=%.8f" % out["piece10"])
 
 
+def density_ratio():
+    """trainers/calibration/density_ratio_calibration.py DensityRatioCalibration.fit/.predict, run unmodified.
+    statsmodels is not installed here: `statsmodels.api` is stubbed so that `sm.nonparametric.KDEMultivariate`
+    resolves to the oracle's restatement of it (published algorithm) - that pins the REFERENCE's arithmetic around
+    the KDE; the KDE restatement itself is cross-checked against sklearn.neighbors.KernelDensity below."""
+    import types
+    stub = types.ModuleType("statsmodels.api")
+    stub.nonparametric = types.SimpleNamespace(KDEMultivariate=orc.KDEMultivariateCC)
+    pkg = types.ModuleType("statsmodels")
+    pkg.api = stub
+    sys.modules.setdefault("statsmodels", pkg)
+    sys.modules.setdefault("statsmodels.api", stub)
+    from trainers.calibration.density_ratio_calibration import DensityRatioCalibration
+    from sklearn.neighbors import KernelDensity
+
+    both = synth.make_case("dr", 1600, 30, 15, 512, 5, 0.22, seed=11)      # one task; rows split into val / test
+    n_val = 1000
+    logits = (torch.tensor(both.logit_scale) * torch.from_numpy(both.img) @ torch.from_numpy(both.txt_tuned).t()).numpy()
+    probs = softmax(logits.astype(np.float64) * 0.5, axis=1).astype(np.float32)
+    val_probs32, test_probs32 = probs[:n_val], probs[n_val:]
+    val_labels, test_labels = both.labels[:n_val], both.labels[n_val:]
+    val_img, test_img = both.img[:n_val], both.img[n_val:]
+    val_prox = np.exp(-np.mean(ref_prox.get_val_image_knn_dists(val_img, 10), axis=-1))      # vl_calibrator.py:68
+    test_prox = np.exp(-np.mean(ref_prox.get_knn_dists(val_img, test_img, 10), axis=-1))     # base_learner.py:137
+    val_preds = np.argmax(val_probs32, axis=1)
+    out = {"val_probs": val_probs32, "val_preds": val_preds, "val_labels": val_labels, "val_prox": val_prox,
+           "test_probs": test_probs32, "test_prox": test_prox, "test_labels": test_labels}
+    for tag, vp, tp in (("f32", val_probs32, test_probs32), ("f64", val_probs32.astype(np.float64), test_probs32.astype(np.float64))):
+        ref = DensityRatioCalibration()
+        ref.fit(vp, val_preds, val_labels, val_prox)
+        got = ref.predict(tp.copy(), test_prox)
+        state = orc.density_ratio_fit(vp, val_preds, val_labels, val_prox)
+        mine, cal = orc.density_ratio_predict(state, tp, test_prox)
+        assert np.array_equal(got, mine), "oracle density_ratio_predict != reference"
+        assert abs(state[2] - ref.false_true_ratio) == 0
+        if tag == "f32":
+            out["f32_probs_out"] = got
+        out[f"{tag}_conf_cal"] = cal
+        out[f"{tag}_bw_true"], out[f"{tag}_bw_false"], out[f"{tag}_ratio"] = state[0].bw, state[1].bw, float(state[2])
+        # independent check of the KDE restatement: isotropic Gaussian KDE on bandwidth-scaled coordinates
+        for dens in state[:2]:
+            kd = KernelDensity(kernel="gaussian", bandwidth=1.0).fit(dens.data / dens.bw)
+            pts = np.array([np.max(tp, axis=-1), test_prox]).T
+            want = np.exp(kd.score_samples(pts / dens.bw)) / np.prod(dens.bw)
+            assert np.allclose(dens.pdf(pts), want, rtol=1e-8, atol=1e-12 * want.max()), "KDE restatement != sklearn KernelDensity"
+    print("density_ratio: n_val=%d (true %d) n_test=%d  mean conf %.6f -> %.6f  acc %.6f" % (
+        len(val_preds), int((val_preds == val_labels).sum()), len(test_labels), float(np.max(test_probs32, 1).mean()),
+        float(out["f64_conf_cal"].mean()), float((np.argmax(test_probs32, 1) == test_labels).mean())))
+    np.savez_compressed(os.path.join(OUT, "density_ratio.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     metric_edge_cases()
     proximity_and_piece()
+    density_ratio()
     run_case("eurosat")
     run_case("sun397_l14", ks=(1, 5, 10))
     run_case("imagenet")

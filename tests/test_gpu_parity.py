@@ -403,3 +403,132 @@ def test_bad_arguments_fail_loudly(cuda_lib):
         bad.predict(np.zeros((2, 3), np.float32))
     with pytest.raises(Exception):
         native.bin_stats(torch.zeros(4), torch.zeros(4, dtype=torch.int32), torch.zeros(4, dtype=torch.int64), [0.5])
+
+
+# ----------------------------------------------------------------------------- f-4 density-ratio calibration
+def test_density_ratio_calibration_matches_reference_fixture(cuda_lib, golden):
+    """DensityRatioCalibration.fit/.predict against what the reference class returned (tests/golden/density_ratio.npz,
+    oracle/make_golden.py) and against the oracle, for float32 and float64 probability matrices."""
+    from clip_calibration_b200.trainers.calibration.density_ratio_calibration import DensityRatioCalibration
+    g = golden("density_ratio")
+    cal = DensityRatioCalibration()
+    cal.fit(g["val_probs"], g["val_preds"], g["val_labels"], g["val_prox"])
+    np.testing.assert_allclose(cal.dens_true.bw, g["f32_bw_true"], rtol=1e-12)
+    np.testing.assert_allclose(cal.dens_false.bw, g["f32_bw_false"], rtol=1e-12)
+    assert float(cal.false_true_ratio) == float(g["f32_ratio"])
+    before = g["test_probs"].copy()
+    out = cal.predict(g["test_probs"], g["test_prox"])
+    assert out.dtype == np.float64 and out.shape == before.shape and np.array_equal(g["test_probs"], before)
+    # tolerance: ex2.approx (2e-7) on float64 exponents; the reference sums the other classes in float32 (1e-7)
+    np.testing.assert_allclose(out, g["f32_probs_out"], rtol=2e-6, atol=1e-300)
+    np.testing.assert_allclose(out.sum(axis=1), 1.0, rtol=1e-6)
+    conf = cal.calibrated_confidence(g["test_probs"].max(axis=1), g["test_prox"])
+    np.testing.assert_allclose(conf, g["f32_conf_cal"], rtol=2e-6, atol=1e-300)
+    # float64 probabilities
+    cal64 = DensityRatioCalibration()
+    cal64.fit(g["val_probs"].astype(np.float64), g["val_preds"], g["val_labels"], g["val_prox"])
+    out64 = cal64.predict(g["test_probs"].astype(np.float64), g["test_prox"])
+    state = orc.density_ratio_fit(g["val_probs"].astype(np.float64), g["val_preds"], g["val_labels"], g["val_prox"])
+    want64, _ = orc.density_ratio_predict(state, g["test_probs"].astype(np.float64), g["test_prox"])
+    np.testing.assert_allclose(out64, want64, rtol=2e-6, atol=1e-300)
+
+
+@pytest.mark.parametrize("m,n,bw", [(1, 5, (0.05, 0.002)), (7, 1, (0.1, 0.1)), (513, 700, (0.03, 0.0007)),
+                                    (20000, 3000, (0.02, 0.001)), (300, 100000, (0.05, 0.003))])
+def test_kde2_pdf_against_float64_oracle(cuda_lib, m, n, bw):
+    """ccal_kde2_pdf against the float64 restatement, including far tails (densities down to 1e-300: the ratio of two
+    such values is what the calibrator uses) and query points that coincide with data points."""
+    rng = np.random.default_rng(m + n)
+    data = np.stack([rng.random(m), 0.4 + 0.01 * rng.standard_normal(m)], axis=1)
+    q = np.stack([rng.random(n), 0.4 + 0.02 * rng.standard_normal(n)], axis=1)
+    q[: min(n, m, 3)] = data[: min(n, m, 3)]
+    if n > 4:
+        q[4] = (0.5, 0.4 + 37 * bw[1])                    # deep tail: exp(-684) ~ 1e-297 still representable
+    dens = orc.KDEMultivariateCC([data[:, 0], data[:, 1]])
+    dens.bw = np.array(bw)
+    sel = np.unique(np.concatenate([np.arange(min(n, 64)), rng.integers(0, n, 64)]))
+    want = dens.pdf(q[sel])
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    got = native.kde2_pdf(dev(data[:, 0]), dev(data[:, 1]), dev(q[:, 0]), dev(q[:, 1]), *bw).cpu().numpy()
+    assert got.shape == (n,) and np.all(np.isfinite(got))
+    np.testing.assert_allclose(got[sel], want, rtol=1e-6, atol=1e-305)
+
+
+@pytest.mark.parametrize("n,c,dtype", [(1, 2, np.float32), (300, 10, np.float32), (77, 397, np.float64), (40, 2049, np.float32),
+                                       (9, 49408, np.float32), (5000, 1000, np.float32)])
+def test_density_ratio_apply_rows(cuda_lib, n, c, dtype):
+    rng = np.random.default_rng(n + c)
+    logits = rng.standard_normal((n, c)) * 3
+    probs = orc.softmax_lastaxis(logits).astype(dtype)
+    if c > 3:
+        probs[0, 1] = probs[0, 3] = probs[0].max()                    # tie: the first maximum is the prediction
+    t = rng.random(n); f = rng.random(n); ratio = 0.37
+    if n > 2:
+        t[1], f[1] = 0.0, 0.0                                          # both densities underflowed: eps floor -> 0
+        t[2], f[2] = 1e-290, 3e-290
+    dens_t = type("D", (), {"pdf": staticmethod(lambda d: t)})
+    dens_f = type("D", (), {"pdf": staticmethod(lambda d: f)})
+    want, wcal = orc.density_ratio_predict((dens_t, dens_f, ratio), probs, np.zeros(n))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    out, cal, pred = native.density_ratio_apply(dev(probs), dev(t), dev(f), ratio)
+    assert np.array_equal(pred.cpu().numpy(), np.argmax(probs, axis=1))
+    np.testing.assert_allclose(cal.cpu().numpy(), wcal, rtol=1e-14, atol=0)
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-6 if dtype == np.float32 else 1e-12, atol=0)
+
+
+def test_vl_calibration_scaling_based_with_proximity(cuda_lib, golden):
+    """VLCalibration(base_calibration_mode='scaling_based', procal_flag=True): softmax -> density-ratio calibrator
+    (reference vl_calibrator.py:95-96, :116-119)."""
+    g = golden("density_ratio")
+    val_logits = np.log(g["val_probs"].astype(np.float64))             # softmax(log p) == p
+    test_logits = np.log(g["test_probs"].astype(np.float64))
+    val_dict = {"val_logits": val_logits, "val_labels": g["val_labels"], "val_image_features": None,
+                "val_text_features": None, "val_image_knn_dists": -np.log(g["val_prox"].astype(np.float64))[:, None]}
+    cal = vl_calibrator.VLCalibration(None, base_calibration_mode="scaling_based", procal_flag=True, val_dict=val_dict)
+    cal.fit()
+    out = cal.predict(test_logits, g["test_prox"])
+    assert out.dtype == np.float64
+    np.testing.assert_allclose(out, g["f32_probs_out"], rtol=5e-5, atol=1e-12)   # probabilities re-derived through log/softmax in fp32
+    with pytest.raises(NotImplementedError):
+        vl_calibrator.VLCalibration(None, base_calibration_mode="bin_based", val_dict=val_dict)
+
+
+# ----------------------------------------------------------------------------- macro-F1 (evaluator)
+@pytest.mark.parametrize("n,c", [(1, 1), (1000, 10), (5000, 397), (200000, 2048), (300000, 49408), (0, 5)])
+def test_class_counts_and_macro_f1(cuda_lib, n, c):
+    import warnings
+    from sklearn.metrics import f1_score
+    rng = np.random.default_rng(n + c)
+    gt = rng.integers(0, c, n)
+    pred = np.where(rng.random(n) < 0.7, gt, rng.integers(0, c, n))
+    counts = metrics.class_counts(pred.astype(np.int32), gt, n_classes=c)
+    want = np.zeros((c, 3), np.int64)
+    np.add.at(want[:, 0], gt[pred == gt], 1)
+    np.add.at(want[:, 1], pred[pred != gt], 1)
+    np.add.at(want[:, 2], gt[pred != gt], 1)
+    assert np.array_equal(counts, want)
+    if n:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = f1_score(gt, pred, average="macro", labels=np.unique(gt))      # evaluators/vl_evaluator.py:74-79
+        assert abs(metrics.macro_f1(pred, gt) - ref) < 1e-12                     # int64 preds, class count inferred
+        # accumulation over shards = one pass (what the multi-GPU path all-reduces)
+        acc = native.class_counts(torch.from_numpy(pred[: n // 2]).cuda(), torch.from_numpy(gt[: n // 2]).cuda(), c)
+        native.class_counts(torch.from_numpy(pred[n // 2:]).cuda(), torch.from_numpy(gt[n // 2:]).cuda(), c, acc)
+        assert np.array_equal(acc.cpu().numpy(), want)
+
+
+def test_evaluator_reports_reference_keys(cuda_lib, golden):
+    from clip_calibration_b200.evaluators import vl_evaluator
+    import warnings
+    from sklearn.metrics import f1_score
+    g = golden("eurosat")
+    case = synth.make_config("eurosat", seed=0)
+    res = vl_evaluator.evaluate_pred_conf(g["dac_pred"], g["dac_conf"], case.labels, 10)
+    for key in ("accuracy", "error_rate", "macro_f1", "confidence", "ece", "mce", "ace"):
+        assert key in res
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        f1 = 100.0 * f1_score(case.labels, g["dac_pred"], average="macro", labels=np.unique(case.labels))
+    assert abs(res["macro_f1"] - f1) < 1e-9
+    assert abs(res["ece"] - 100.0 * float(g["dac_ece10"])) < 1e-5

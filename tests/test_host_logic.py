@@ -186,3 +186,43 @@ def test_tempscaling_surface_without_dassl(tmp_path):
         ts.load_logit_scale(str(tmp_path), 99)
     with pytest.raises(ImportError):
         ts.TempScaling()                       # the trainer itself needs dassl
+
+
+def test_macro_f1_from_counts_matches_sklearn():
+    import warnings
+    from sklearn.metrics import f1_score
+    rng = np.random.default_rng(0)
+    for c, n in ((5, 100), (50, 300), (397, 2000), (3, 10)):
+        gt = rng.integers(0, c, n)
+        pred = np.where(rng.random(n) < 0.6, gt, rng.integers(0, c + 3, n))      # some predictions outside the label set
+        counts = np.zeros((int(max(gt.max(), pred.max())) + 1, 3), np.int64)
+        for p, g in zip(pred, gt):
+            if p == g:
+                counts[g, 0] += 1
+            else:
+                counts[p, 1] += 1
+                counts[g, 2] += 1
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = f1_score(gt, pred, average="macro", labels=np.unique(gt))     # evaluators/vl_evaluator.py:74-79
+        assert abs(tm.macro_f1_from_counts(counts) - want) < 1e-12
+    assert tm.macro_f1_from_counts(np.zeros((4, 3))) == 0.0
+
+
+def test_reliability_diagram_data_from_table(golden):
+    """tools/plot.py:11-36 arrays from an (n+1)-bin table (here built by the oracle's bin_table)."""
+    from clip_calibration_b200.tools import plot
+    g = golden("metric_edge_cases")
+    for name in ("saturated", "on_edges", "narrow"):
+        conf, pred, gt = g[f"{name}_conf"], g[f"{name}_pred"], g[f"{name}_gt"]
+        for nb in (10, 15):
+            table = orc.bin_table(conf, pred, gt, tm.uniform_thresholds(nb))
+            d = plot.reliability_diagram_data(None, None, None, nb, table=table)
+            bins = np.linspace(0, 1, nb + 1)
+            idx = np.digitize(conf, bins) - 1
+            acc = np.array([np.mean(gt[idx == i] == pred[idx == i]) if np.any(idx == i) else 0 for i in range(nb)])
+            cf = np.array([np.mean(conf[idx == i]) if np.any(idx == i) else 0 for i in range(nb)])
+            np.testing.assert_allclose(d["bin_acc"], acc, rtol=1e-12)
+            np.testing.assert_allclose(d["bin_confidences"], cf, rtol=1e-6)
+            np.testing.assert_allclose(d["weights"], np.histogram(conf, bins)[0] / len(conf), rtol=1e-12)
+            assert abs(d["ece"] - float(g[f"{name}_ece{nb}"])) < 1e-7

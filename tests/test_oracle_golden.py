@@ -71,3 +71,21 @@ def test_ts_loss_grad_against_finite_difference():
     lp, _ = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t + 1e-5)
     lm, _ = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t - 1e-5)
     assert abs((lp - lm) / 2e-5 - grad) < 1e-6 * max(1.0, abs(grad))
+
+
+def test_density_ratio_matches_reference(golden):
+    """The fixture holds what the reference's DensityRatioCalibration.fit/.predict returned (oracle/make_golden.py)."""
+    g = golden("density_ratio")
+    state = orc.density_ratio_fit(g["val_probs"], g["val_preds"], g["val_labels"], g["val_prox"])
+    np.testing.assert_allclose(state[0].bw, g["f32_bw_true"], rtol=1e-13)
+    np.testing.assert_allclose(state[1].bw, g["f32_bw_false"], rtol=1e-13)
+    assert state[2] == float(g["f32_ratio"])
+    out, cal = orc.density_ratio_predict(state, g["test_probs"], g["test_prox"])
+    np.testing.assert_allclose(cal, g["f32_conf_cal"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(out, g["f32_probs_out"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(out.sum(axis=1), 1.0, rtol=1e-6)
+    # float64 probabilities (the no-DAC branch keeps float64): same calibrated confidences here because the
+    # fixture's float64 case is the float32 matrix widened
+    state64 = orc.density_ratio_fit(g["val_probs"].astype(np.float64), g["val_preds"], g["val_labels"], g["val_prox"])
+    _, cal64 = orc.density_ratio_predict(state64, g["test_probs"].astype(np.float64), g["test_prox"])
+    np.testing.assert_allclose(cal64, g["f64_conf_cal"], rtol=1e-12, atol=0)
