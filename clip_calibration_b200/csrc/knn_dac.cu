@@ -16,7 +16,7 @@
 namespace ccal {
 
 constexpr int kTile = 64;        // queries per CTA and references per tile
-constexpr int kChunk = 16;       // feature chunk
+constexpr int kChunk = 32;       // feature chunk (multiple of 16)
 constexpr int kPad = 68;         // padded row length of the transposed chunks
 constexpr int kRowsPerWarp = 8;
 constexpr int kMaxList = CCAL_MAX_K + 1;
@@ -72,19 +72,34 @@ knn_l2_kernel(const float* __restrict__ ref, const float* __restrict__ query, lo
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
 
-    for (int d0 = 0; d0 < d; d0 += kChunk) {
-      float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), rv = qv;
-      const int dc = d0 + ld_col;
-      if (dc < d) {                                     // d % 4 == 0 is required by the host
-        if (ld_q >= 0) qv = *reinterpret_cast<const float4*>(query + ld_q * d + dc);
-        if (r0 + ld_row < nr) rv = *reinterpret_cast<const float4*>(ref + (r0 + ld_row) * d + dc);
+    // software pipeline: the next feature chunk is loaded into registers while the current one is consumed from
+    // shared memory, so the global-load latency is paid once per tile instead of once per chunk
+    float4 qv[kChunk / 16], rv[kChunk / 16];
+    auto load_chunk = [&](int d0) {
+#pragma unroll
+      for (int h = 0; h < kChunk / 16; ++h) {
+        qv[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rv[h] = qv[h];
+        const int dc = d0 + 16 * h + ld_col;
+        if (dc < d) {                                   // d % 4 == 0 is required by the host
+          if (ld_q >= 0) qv[h] = *reinterpret_cast<const float4*>(query + ld_q * d + dc);
+          if (r0 + ld_row < nr) rv[h] = *reinterpret_cast<const float4*>(ref + (r0 + ld_row) * d + dc);
+        }
       }
+    };
+    load_chunk(0);
+    for (int d0 = 0; d0 < d; d0 += kChunk) {
       __syncthreads();                                   // previous chunk fully consumed
-      Qs[ld_col + 0][ld_row] = qv.x; Qs[ld_col + 1][ld_row] = qv.y;
-      Qs[ld_col + 2][ld_row] = qv.z; Qs[ld_col + 3][ld_row] = qv.w;
-      Rs[ld_col + 0][ld_row] = rv.x; Rs[ld_col + 1][ld_row] = rv.y;
-      Rs[ld_col + 2][ld_row] = rv.z; Rs[ld_col + 3][ld_row] = rv.w;
+#pragma unroll
+      for (int h = 0; h < kChunk / 16; ++h) {
+        const int c0 = 16 * h + ld_col;
+        Qs[c0 + 0][ld_row] = qv[h].x; Qs[c0 + 1][ld_row] = qv[h].y;
+        Qs[c0 + 2][ld_row] = qv[h].z; Qs[c0 + 3][ld_row] = qv[h].w;
+        Rs[c0 + 0][ld_row] = rv[h].x; Rs[c0 + 1][ld_row] = rv[h].y;
+        Rs[c0 + 2][ld_row] = rv[h].z; Rs[c0 + 3][ld_row] = rv[h].w;
+      }
       __syncthreads();
+      if (d0 + kChunk < d) load_chunk(d0 + kChunk);
 #pragma unroll
       for (int kk = 0; kk < kChunk; ++kk) {
         const float4 q4 = *reinterpret_cast<const float4*>(&Qs[kk][ty * 4]);
@@ -197,13 +212,21 @@ knn_redo_scan_kernel(const float* __restrict__ ref, const float* __restrict__ qu
         const float4* rv = reinterpret_cast<const float4*>(ref + r * d);
         const float4* qv = reinterpret_cast<const float4*>(s_q);
         float acc = 0.f;
-#pragma unroll 16
-        for (int j = 0; j < d / 4; ++j) {
-          const float4 a = qv[j], b = __ldg(rv + j);
-          float df = b.x - a.x; acc = fmaf(df, df, acc);
-          df = b.y - a.y; acc = fmaf(df, df, acc);
-          df = b.z - a.z; acc = fmaf(df, df, acc);
-          df = b.w - a.w; acc = fmaf(df, df, acc);
+        const int d4 = d >> 2;
+        for (int j0 = 0; j0 < d4; j0 += 16) {
+          float4 b[16];                                 // sixteen loads issued before the first use
+#pragma unroll
+          for (int u = 0; u < 16; ++u) b[u] = (j0 + u < d4) ? __ldg(rv + j0 + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            if (j0 + u < d4) {
+              const float4 a = qv[j0 + u];
+              float df = b[u].x - a.x; acc = fmaf(df, df, acc);
+              df = b[u].y - a.y; acc = fmaf(df, df, acc);
+              df = b[u].z - a.z; acc = fmaf(df, df, acc);
+              df = b[u].w - a.w; acc = fmaf(df, df, acc);
+            }
+          }
         }
         dist = sqrtf(acc);
       }

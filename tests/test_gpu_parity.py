@@ -132,6 +132,27 @@ def test_knn_tensor_core_filter_equals_exhaustive_scan(cuda_lib, nr, nq, d, k, d
     np.testing.assert_allclose(d_tc[rows].cpu().numpy(), ref_d, rtol=3e-6, atol=3e-7)
 
 
+@pytest.mark.parametrize("nr,nq,d,k,drop", [(5, 10, 512, 5, False), (199, 397, 768, 10, False), (500, 1000, 512, 5, False),
+                                             (64, 16000, 64, 16, False), (1, 50, 4, 1, False), (300, 300, 128, 5, True),
+                                             (3, 9, 1024, 7, False), (1000, 1000, 20, 16, True)])
+def test_knn_small_problems_equal_exhaustive_scan(cuda_lib, nr, nq, d, k, drop):
+    """Small shapes (below / around the switch between the exhaustive scan and the tensor-core filter): ccal_knn_l2 must
+    return what the exhaustive scan returns, ties to the lowest index, k > nr padded."""
+    g = torch.Generator(device="cuda").manual_seed(nr * 7 + nq)
+    ref = torch.nn.functional.normalize(torch.randn(nr, d, device="cuda", generator=g) + 1.0, dim=-1)
+    if nr > 4:
+        ref[3] = ref[1]                                                # duplicate reference rows: equal distances
+    qry = ref if drop else torch.nn.functional.normalize(torch.randn(nq, d, device="cuda", generator=g) + 1.0, dim=-1)
+    d_s, i_s = native.knn_l2(ref, qry, k, drop)
+    d_ex, i_ex = native.knn_l2(ref, qry, k, drop, exhaustive=True)
+    torch.testing.assert_close(d_s, d_ex, rtol=2e-6, atol=2e-7)
+    diff = i_s != i_ex
+    if diff.any():                                         # only where two distances coincide to rounding
+        assert float((d_s[diff] - d_ex[diff]).abs().max()) <= 1e-6
+    want = orc.knn_dists(ref.cpu().numpy(), qry[:32].cpu().numpy(), min(k, nr - (1 if drop else 0)), drop_self=drop)
+    np.testing.assert_allclose(d_s[:32, : want.shape[1]].cpu().numpy(), want, rtol=3e-6, atol=3e-7)
+
+
 def test_knn_tensor_core_falls_back_on_ties_and_wild_norms(cuda_lib):
     g = torch.Generator(device="cuda").manual_seed(5)
     base = torch.nn.functional.normalize(torch.randn(40, 128, device="cuda", generator=g), dim=-1)
