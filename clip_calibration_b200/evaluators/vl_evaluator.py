@@ -18,18 +18,25 @@ from .. import table_math as tm
 from ..tools import metrics
 
 
-def evaluate_pred_conf(preds, confs, labels, ece_bins: int = 10, piece_bins: int = 10, proximity=None,
-                       group=None, n_classes=None) -> "OrderedDict[str, float]":
-    """Metrics from per-image (pred, conf, label); numpy or CUDA tensors."""
-    table = metrics.bin_stats(confs, preds, labels, ece_bins, group)
+def results_from_tables(table, class_counts) -> "OrderedDict[str, float]":
+    """accuracy / error_rate / macro_f1 / confidence / ece / mce (reference keys and units) from the (n+1)-bin table
+    and the per-class {tp, fp, fn} counts - everything that needs no second pass over the images."""
     results = OrderedDict()
     acc = 100.0 * tm.accuracy(table)
     results["accuracy"] = acc
     results["error_rate"] = 100.0 - acc
-    results["macro_f1"] = 100.0 * metrics.macro_f1(preds, labels, n_classes, group)
+    results["macro_f1"] = 100.0 * tm.macro_f1_from_counts(class_counts)
     results["confidence"] = tm.mean_confidence(table)
     results["ece"] = 100.0 * float(tm.ece_from_table(table))
     results["mce"] = 100.0 * float(tm.mce_from_table(table))
+    return results
+
+
+def evaluate_pred_conf(preds, confs, labels, ece_bins: int = 10, piece_bins: int = 10, proximity=None,
+                       group=None, n_classes=None) -> "OrderedDict[str, float]":
+    """Metrics from per-image (pred, conf, label); numpy or CUDA tensors."""
+    table = metrics.bin_stats(confs, preds, labels, ece_bins, group)
+    results = results_from_tables(table, metrics.class_counts(preds, labels, n_classes, group))
     results["ace"] = 100.0 * float(metrics.AdaptiveECE(confs, preds, labels, ece_bins, group=group))
     if proximity is not None:
         results["piece"] = 100.0 * float(metrics.PIECE(confs, proximity, preds, labels, piece_bins, ece_bins,

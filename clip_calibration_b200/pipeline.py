@@ -31,7 +31,7 @@ class CalibratedScorer:
     """Text side of the problem, resident on this rank's GPU, plus the running bin table."""
 
     def __init__(self, text_features, class_conf=None, logit_scale: float = 100.0, n_bins: int = 10,
-                 operand_dtype=None, group=None, device=None):
+                 operand_dtype=None, group=None, device=None, keep_outputs: bool = False):
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         probe = text_features if isinstance(text_features, torch.Tensor) else torch.from_numpy(np.asarray(text_features)[:1])
         self.operand_dtype = native.operand_dtype_for(probe, operand_dtype)
@@ -47,6 +47,11 @@ class CalibratedScorer:
         self.table = native.new_table(self.n_bins, device=self.device)
         self._copy_stream = None
         self._pending_img, self._pending_lab, self._pending_rows = [], [], 0
+        # evaluator mode: per-image (pred, conf, label) stay on the device (16 B/image) and per-class {tp, fp, fn}
+        # are counted, so that evaluate() can report every key of the reference's evaluator (macro-F1, ACE, PIECE)
+        self.keep_outputs = bool(keep_outputs)
+        self._kept = []                       # [(pred int32, conf float32, labels int64)] per scored shard
+        self.class_counts = None
 
     # ------------------------------------------------------------------ construction helpers
     def _features(self, x) -> torch.Tensor:
@@ -70,6 +75,13 @@ class CalibratedScorer:
     def reset(self):
         self.table.zero_()
         self._pending_img, self._pending_lab, self._pending_rows = [], [], 0
+        self._kept, self.class_counts = [], None
+
+    def _keep(self, pred, conf, labels) -> None:
+        if self.class_counts is None:
+            self.class_counts = torch.zeros((self.txt.shape[0], 3), dtype=torch.int64, device=self.device)
+        native.class_counts(pred, labels, self.txt.shape[0], self.class_counts)
+        self._kept.append((pred, conf, labels))
 
     def score(self, image_features, labels=None, accumulate: bool = True):
         """Device-resident shard -> (pred, conf); with labels the shard is also binned into the
@@ -81,6 +93,8 @@ class CalibratedScorer:
         use_table = labels is not None and accumulate
         pred, conf, _ = native.score_fused(img, self.txt, self.class_conf, self.logit_scale, labels,
                                            self.thresholds if use_table else None, self.table if use_table else None)
+        if use_table and self.keep_outputs:
+            self._keep(pred, conf, labels)
         return pred, conf
 
     def add(self, image_features, labels, flush_rows: int = 32768) -> None:
@@ -101,8 +115,10 @@ class CalibratedScorer:
             img = torch.cat(self._pending_img) if len(self._pending_img) > 1 else self._pending_img[0]
             lab = torch.cat(self._pending_lab) if len(self._pending_lab) > 1 else self._pending_lab[0]
             self._pending_img, self._pending_lab, self._pending_rows = [], [], 0
-            native.score_fused(img, self.txt, self.class_conf, self.logit_scale, lab, self.thresholds, self.table,
-                               want_pred=False, want_conf=False)
+            pred, conf, _ = native.score_fused(img, self.txt, self.class_conf, self.logit_scale, lab, self.thresholds,
+                                               self.table, want_pred=self.keep_outputs, want_conf=self.keep_outputs)
+            if self.keep_outputs:
+                self._keep(pred, conf, lab)
 
     def accumulate_host(self, image_features: torch.Tensor, labels: torch.Tensor, chunk_rows: int = 131072,
                         keep_outputs: bool = False, ramp: bool = True):
@@ -146,7 +162,10 @@ class CalibratedScorer:
             comp.wait_event(copied[b])
             pred, conf, _ = native.score_fused(bufs[b][: hi - lo], self.txt, self.class_conf, self.logit_scale,
                                                lbufs[b][: hi - lo], self.thresholds, self.table,
-                                               want_pred=keep_outputs, want_conf=keep_outputs)
+                                               want_pred=keep_outputs or self.keep_outputs,
+                                               want_conf=keep_outputs or self.keep_outputs)
+            if self.keep_outputs:
+                self._keep(pred, conf, lbufs[b][: hi - lo].clone())
             consumed[b].record(comp)
             if keep_outputs:
                 preds.append(pred)
@@ -166,6 +185,40 @@ class CalibratedScorer:
             t = t.clone()
             torch.distributed.all_reduce(t, group=self.group)
         return native.table_to_numpy(t)
+
+    def _reduce_group(self):
+        """The process group the tables are reduced over, or None when there is nothing to reduce."""
+        if self.group is False or not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return None
+        group = self.group if self.group is not None else torch.distributed.group.WORLD
+        return group if torch.distributed.get_world_size(group) > 1 else None
+
+    def evaluate(self, proximity=None, piece_bins: int = 10) -> dict:
+        """Every key of the reference's `VLClassification.evaluate` result (evaluators/vl_evaluator.py:59-116), as
+        percentages, from the fused path: accuracy / error_rate / confidence / ece / mce from the bin table, macro_f1
+        from the per-class counts, ace (and piece when `proximity` [N] for this rank's images, in scoring order, is
+        given) from the kept per-image confidences.  Needs keep_outputs=True.  Multi-GPU: all ranks call it together."""
+        if not self.keep_outputs:
+            raise RuntimeError("evaluate() needs CalibratedScorer(..., keep_outputs=True); summary() works without")
+        from .evaluators.vl_evaluator import results_from_tables
+        from .tools import metrics
+        table = self.reduced_table()                      # flushes pending batches
+        group = self._reduce_group()
+        if self.class_counts is None:
+            self.class_counts = torch.zeros((self.txt.shape[0], 3), dtype=torch.int64, device=self.device)
+        counts = self.class_counts.clone()
+        if group is not None:
+            torch.distributed.all_reduce(counts, group=group)
+        cat = lambda i, dt: (torch.cat([k[i] for k in self._kept]) if self._kept
+                             else torch.empty(0, dtype=dt, device=self.device))
+        pred, conf, labels = cat(0, torch.int32), cat(1, torch.float32), cat(2, torch.int64)
+        results = results_from_tables(table, counts.cpu().numpy())
+        results["ace"] = 100.0 * float(metrics.AdaptiveECE(conf, pred, labels, self.n_bins, group=group))
+        if proximity is not None:
+            results["piece"] = 100.0 * float(metrics.PIECE(conf, proximity, pred, labels, piece_bins, self.n_bins,
+                                                           group=group))
+        results["bin_table"] = table
+        return results
 
     def summary(self) -> dict:
         table = self.reduced_table()

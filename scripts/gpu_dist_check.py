@@ -2,7 +2,9 @@
   - every rank scores its image shard (fused kernel) into an integer bin table; ONE all-reduce must
     reproduce, bit for bit, the table rank 0 gets by scoring all images alone;
   - AdaptiveECE / PIECE with `group=` (all-reduced radix histograms -> global quantile edges) must equal
-    the single-GPU values on the gathered arrays.
+    the single-GPU values on the gathered arrays;
+  - CalibratedScorer(keep_outputs=True).evaluate() (bin table + per-class counts all-reduced, global quantile edges)
+    must report on N ranks what one rank reports alone, macro-F1 included.
 Prints one JSON line from rank 0; exits non-zero on any mismatch."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -30,6 +32,11 @@ ace = float(metrics.AdaptiveECE(conf, pred, labels_dev, 10, group=dist.group.WOR
 piece = float(metrics.PIECE(conf, torch.from_numpy(prox_all[lo:hi]).cuda(), pred, labels_dev, 10, 10, group=dist.group.WORLD))
 ece = float(metrics.ECE(conf, pred, labels_dev, 10, group=dist.group.WORLD))
 
+ev_scorer = pipeline.CalibratedScorer(case.txt_tuned, scorer.class_conf, 100.0, 10, keep_outputs=True)
+ev_scorer.score(case.img[lo:hi], case.labels[lo:hi])
+ev = ev_scorer.evaluate(proximity=torch.from_numpy(prox_all[lo:hi]).cuda())
+f1 = float(metrics.macro_f1(pred, labels_dev, n_classes=1000, group=dist.group.WORLD))
+
 ok = True
 if rank == 0:
     solo = pipeline.CalibratedScorer(case.txt_tuned, scorer.class_conf, 100.0, 10)
@@ -42,6 +49,13 @@ if rank == 0:
     piece1 = float(metrics.PIECE(c_all, torch.from_numpy(prox_all).cuda(), p_all, lab_all, 10, 10))
     ece1 = float(tm.ece_from_table(full))
     ok &= abs(ace - ace1) < 1e-12 and abs(piece - piece1) < 1e-12 and abs(ece - ece1) < 1e-12
+    solo_ev = pipeline.CalibratedScorer(case.txt_tuned, scorer.class_conf, 100.0, 10, keep_outputs=True, group=False)
+    solo_ev.score(case.img, case.labels)
+    ev1 = solo_ev.evaluate(proximity=torch.from_numpy(prox_all).cuda())
+    keys = ("accuracy", "error_rate", "macro_f1", "confidence", "ece", "mce", "ace", "piece")
+    ev_ok = all(abs(ev[k] - ev1[k]) < 1e-9 for k in keys) and abs(100.0 * f1 - ev1["macro_f1"]) < 1e-9
+    ok &= ev_ok
+    print(json.dumps({"evaluate_identical": bool(ev_ok), "macro_f1": [ev["macro_f1"], ev1["macro_f1"]]}), file=sys.stderr)
     print(json.dumps({"world": world, "tables_identical": bool(np.array_equal(full, reduced)), "ece": [ece, ece1],
                       "ace": [ace, ace1], "piece": [piece, piece1], "ok": bool(ok)}), flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")

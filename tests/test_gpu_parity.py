@@ -553,3 +553,38 @@ def test_evaluator_reports_reference_keys(cuda_lib, golden):
         f1 = 100.0 * f1_score(case.labels, g["dac_pred"], average="macro", labels=np.unique(case.labels))
     assert abs(res["macro_f1"] - f1) < 1e-9
     assert abs(res["ece"] - 100.0 * float(g["dac_ece10"])) < 1e-5
+
+
+def test_scorer_evaluate_reports_every_reference_key(cuda_lib, golden):
+    """CalibratedScorer(keep_outputs=True).evaluate(): the fused path must reproduce the evaluator's result dict
+    (evaluators/vl_evaluator.py:59-116) computed from the reference fixture's per-image outputs."""
+    import warnings
+    from sklearn.metrics import f1_score
+    from clip_calibration_b200.evaluators import vl_evaluator
+    g = golden("sun397_l14")
+    case = synth.make_config("sun397_l14", seed=0)
+    prox = np.random.default_rng(3).random(case.img.shape[0]).astype(np.float32)
+    scorer = pipeline.CalibratedScorer.from_dac(case.base_zs, case.txt_zs, case.base_tuned, case.txt_tuned, k=5,
+                                                logit_scale=case.logit_scale, operand_dtype=torch.bfloat16,
+                                                keep_outputs=True, group=False)
+    n = case.img.shape[0]
+    # three entry points, in order: per-batch add(), a device shard, a pinned host shard
+    a, b = n // 3, 2 * n // 3
+    for lo in range(0, a, 1000):
+        scorer.add(case.img[lo:min(a, lo + 1000)], case.labels[lo:min(a, lo + 1000)], flush_rows=4096)
+    scorer.flush()
+    scorer.score(case.img[a:b], case.labels[a:b])
+    scorer.accumulate_host(torch.from_numpy(case.img[b:]).to(torch.bfloat16).pin_memory(),
+                           torch.from_numpy(case.labels[b:]).pin_memory(), chunk_rows=2048)
+    res = scorer.evaluate(proximity=prox)
+    want = vl_evaluator.evaluate_pred_conf(g["dac_pred"], g["dac_conf"], case.labels, 10, 10, proximity=prox)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        f1 = 100.0 * f1_score(case.labels, g["dac_pred"], average="macro", labels=np.unique(case.labels))
+    assert abs(res["macro_f1"] - f1) < 1e-9
+    for key in ("accuracy", "error_rate", "macro_f1", "confidence", "ece", "mce", "ace", "piece"):
+        assert abs(res[key] - want[key]) < 2e-3, (key, res[key], want[key])      # percent; conf rel 1e-4 -> ECE 1e-5
+    assert abs(res["ece"] - 100.0 * float(g["dac_ece10"])) < 1e-3
+    assert abs(res["ace"] - 100.0 * float(g["dac_ace10"])) < 1e-3
+    with pytest.raises(RuntimeError):
+        pipeline.CalibratedScorer(case.txt_tuned, None, group=False).evaluate()
