@@ -39,6 +39,9 @@ SIGNATURES = {
                                c_void_p, POINTER(c_double), c_int, c_void_p, c_void_p]),
     "ccal_radix_hist": (c_int, [c_void_p, c_int64, c_int, POINTER(c_uint32), c_int, c_void_p, c_void_p]),
     "ccal_class_counts": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "ccal_exp_normalise_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ccal_isotonic_fit_binary": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, POINTER(c_int64), c_void_p]),
+    "ccal_isotonic_transform": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_double, c_void_p, c_void_p]),
     "ccal_kde2_pdf": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p,
                               c_void_p]),
     "ccal_density_ratio_apply": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_double, c_void_p,

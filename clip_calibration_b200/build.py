@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libccal.so")
 STAMP = os.path.join(HERE, ".libccal.stamp")
 
-SOURCES = ["ccal_api.cu", "bin_stats.cu", "logits_ops.cu", "knn_dac.cu", "knn_tc.cu", "score_fused.cu", "density_ratio.cu"]
+SOURCES = ["ccal_api.cu", "bin_stats.cu", "logits_ops.cu", "knn_dac.cu", "knn_tc.cu", "score_fused.cu", "density_ratio.cu", "isotonic.cu"]
 HEADERS = ["ccal_common.cuh", "sm100_ptx.cuh"]
 
 NVCC_FLAGS = [

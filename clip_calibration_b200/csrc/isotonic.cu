@@ -1,0 +1,303 @@
+// f-4: multi-class isotonic-regression calibrator, reference trainers/calibration/multi_isotonic_regression.py
+// (`IsotonicRegression(out_of_bounds='clip').fit_transform(p.flatten(), onehot.flatten())`, scikit-learn) and its
+// proximity-binned wrapper BinMeanShift (multi_proximity_isotonic.py:130-247).
+//
+//   exp_normalise_rows   p = exp(v) / sum(exp(v)) per row in float64, no max shift - the reference's own formula
+//                        (multi_isotonic_regression.py:26, :33) - and the flattened one-hot targets.
+//   isotonic_fit_binary  scikit-learn's `_build_y` for 0/1 targets: sort by x (cub radix sort), merge equal x
+//                        (`_make_unique`: a new value starts where x grows by >= 1e-15), pool adjacent violators,
+//                        drop interior points of constant stretches -> knots (X_thresholds_, y_thresholds_).
+//   isotonic_transform   clip to [X_min_, X_max_], linear interpolation between knots (scipy interp1d), plus the
+//                        reference's `+ 1e-9 * p` term.  HBM-bound, 16 B per element.
+//
+// Pool-adjacent-violators is sequential as written in scikit-learn (_isotonic.pyx); here it runs in ROUNDS: every
+// maximal run of blocks whose means do not strictly increase is pooled into one block, until no run is left.  The
+// fixed point is the same isotonic fit (pooling a non-increasing run is forced); ~10 rounds for 2M points.  Targets
+// are 0/1, so a block is the integer pair (ones, count): comparisons are exact cross-multiplications and the fitted
+// value is one correctly rounded division - there is no summation order to worry about.
+#include "ccal_common.cuh"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <math_constants.h>
+
+namespace ccal {
+
+constexpr int kIsoThreads = 256;
+constexpr double kUniqueEps = 1e-15;        // np.finfo(np.float64).resolution, sklearn _make_unique
+
+static inline unsigned iso_grid(long long n) {
+  return (unsigned)std::min<long long>((n + kIsoThreads - 1) / kIsoThreads, 1 << 20);
+}
+
+// ---------------------------------------------------------------------------------------- rows
+template <typename T, int GROUP>
+__global__ void __launch_bounds__(256)
+exp_normalise_rows_kernel(const T* __restrict__ v, long long n, int c, double* __restrict__ out,
+                          const long long* __restrict__ labels, unsigned char* __restrict__ onehot) {
+  __shared__ double s_sum[8];
+  constexpr int kRowsPerCta = 256 / GROUP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = threadIdx.x % GROUP;
+  const long long stride = (long long)gridDim.x * kRowsPerCta;
+  const long long sweeps = (n + stride - 1) / stride;
+  for (long long sweep = 0; sweep < sweeps; ++sweep) {
+    const long long row = (long long)blockIdx.x * kRowsPerCta + threadIdx.x / GROUP + sweep * stride;
+    const bool live = row < n;
+    const T* x = v + (live ? row : 0) * (long long)c;
+    double sum = 0.0;
+    if (live)
+      for (int j = t; j < c; j += GROUP) sum += exp((double)x[j]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (GROUP > 32) {
+      if (lane == 0) s_sum[warp] = sum;
+      __syncthreads();
+      sum = 0.0;
+      for (int w = 0; w < 8; ++w) sum += s_sum[w];
+      __syncthreads();
+    }
+    if (!live) continue;
+    const long long lab = labels ? labels[row] : -1;
+    for (int j = t; j < c; j += GROUP) {
+      out[row * (long long)c + j] = exp((double)x[j]) / sum;
+      if (onehot) onehot[row * (long long)c + j] = (unsigned char)(lab == j);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- fit
+__global__ void iso_unique_flags_kernel(const double* __restrict__ xs, long long n, int* __restrict__ flag) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    flag[i] = (i == 0 || xs[i] - xs[i - 1] >= kUniqueEps) ? 1 : 0;
+}
+
+// gid = inclusive scan of the flags (1-based group number)
+__global__ void iso_group_kernel(const double* __restrict__ xs, const unsigned char* __restrict__ ys,
+                                 const int* __restrict__ flag, const int* __restrict__ gid, long long n,
+                                 double* __restrict__ ux, unsigned long long* __restrict__ ones,
+                                 unsigned long long* __restrict__ cnt, int* __restrict__ start) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int g = gid[i] - 1;
+    if (flag[i]) { ux[g] = xs[i]; start[g] = g; }
+    if (ys[i]) atomicAdd(&ones[g], 1ull);
+    atomicAdd(&cnt[g], 1ull);
+  }
+}
+
+// head[j] = block j starts a new pooled block: j == 0 or mean(j-1) < mean(j) strictly
+__global__ void iso_heads_kernel(const unsigned long long* __restrict__ ones, const unsigned long long* __restrict__ cnt,
+                                 int nb, int* __restrict__ head, int* __restrict__ any_violation) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nb) return;
+  int h = 1;
+  if (j > 0) {
+    // mean(j-1) >= mean(j)  <=>  ones[j-1] * cnt[j] >= ones[j] * cnt[j-1]   (exact: both factors < 2^31)
+    const bool violation = ones[j - 1] * cnt[j] >= ones[j] * cnt[j - 1];
+    if (violation) { h = 0; *any_violation = 1; }
+  }
+  head[j] = h;
+}
+
+__global__ void iso_pool_kernel(const unsigned long long* __restrict__ ones, const unsigned long long* __restrict__ cnt,
+                                const int* __restrict__ start, const int* __restrict__ head, const int* __restrict__ bid,
+                                int nb, unsigned long long* __restrict__ ones_out, unsigned long long* __restrict__ cnt_out,
+                                int* __restrict__ start_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nb) return;
+  const int b = bid[j] - 1;
+  if (head[j]) start_out[b] = start[j];
+  atomicAdd(&ones_out[b], ones[j]);
+  atomicAdd(&cnt_out[b], cnt[j]);
+}
+
+// fitted value of every unique x: its block = the last one whose first group is <= g
+__global__ void iso_expand_kernel(const unsigned long long* __restrict__ ones, const unsigned long long* __restrict__ cnt,
+                                  const int* __restrict__ start, int nb, int n_groups, double* __restrict__ fy) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  int lo = 0, hi = nb - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (start[mid] <= g) lo = mid; else hi = mid - 1;
+  }
+  fy[g] = (double)ones[lo] / (double)cnt[lo];
+}
+
+// sklearn _build_y, trim_duplicates: drop interior points equal to both neighbours
+__global__ void iso_keep_kernel(const double* __restrict__ fy, int n_groups, unsigned char* __restrict__ keep) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  keep[g] = (g == 0 || g == n_groups - 1 || fy[g] != fy[g - 1] || fy[g] != fy[g + 1]) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------- transform
+__global__ void __launch_bounds__(kIsoThreads)
+iso_transform_kernel(const double* __restrict__ kx, const double* __restrict__ ky, int nk, const double* __restrict__ t,
+                     long long n, double residual_scale, double* __restrict__ out) {
+  const double x_min = kx[0], x_max = kx[nk - 1];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double v = t[i];
+    double r;
+    if (nk == 1) {
+      r = ky[0];
+    } else {
+      const double x = fmin(fmax(v, x_min), x_max);               // out_of_bounds='clip'
+      int lo = 0, hi = nk;                                         // searchsorted(kx, x, side='left')
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (kx[mid] < x) lo = mid + 1; else hi = mid;
+      }
+      const int idx = min(max(lo, 1), nk - 1);
+      const double x0 = kx[idx - 1], x1 = kx[idx], y0 = ky[idx - 1], y1 = ky[idx];
+      const double slope = (y1 - y0) / (x1 - x0);
+      r = slope * (x - x0) + y0;                                   // scipy interp1d, kind='linear'
+    }
+    out[i] = r + residual_scale * v;
+  }
+}
+
+struct HostPair { int any_violation; int last_bid; };
+
+}  // namespace ccal
+
+using namespace ccal;
+
+extern "C" int ccal_exp_normalise_rows(const float* v_f32, const double* v_f64, int64_t n, int c, double* out,
+                                       const int64_t* labels, unsigned char* onehot_out, ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE((v_f32 != nullptr) != (v_f64 != nullptr), "ccal_exp_normalise_rows: exactly one of v_f32 / v_f64 must be given");
+  CCAL_REQUIRE(n >= 0 && c >= 1, "ccal_exp_normalise_rows: bad shape n=%lld c=%d", (long long)n, c);
+  CCAL_REQUIRE(out != nullptr, "ccal_exp_normalise_rows: out is NULL");
+  CCAL_REQUIRE((labels == nullptr) == (onehot_out == nullptr), "ccal_exp_normalise_rows: labels and onehot_out go together");
+  if (n == 0) return CCAL_OK;
+  const long long cap = (long long)num_sms() * 8;
+  const long long* lab = reinterpret_cast<const long long*>(labels);
+#define CCAL_LAUNCH_EXPN(T, ptr)                                                                                        \
+  do {                                                                                                                  \
+    if (c <= 2048)                                                                                                      \
+      exp_normalise_rows_kernel<T, 32><<<(int)std::min<long long>((n + 7) / 8, cap), 256, 0, stream>>>(ptr, n, c, out, lab, onehot_out); \
+    else                                                                                                                \
+      exp_normalise_rows_kernel<T, 256><<<(int)std::min<long long>(n, cap), 256, 0, stream>>>(ptr, n, c, out, lab, onehot_out);          \
+  } while (0)
+  if (v_f32) CCAL_LAUNCH_EXPN(float, v_f32); else CCAL_LAUNCH_EXPN(double, v_f64);
+#undef CCAL_LAUNCH_EXPN
+  note_launch();
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}
+
+extern "C" int ccal_isotonic_fit_binary(const double* x, const unsigned char* y, int64_t n, double* knots_x,
+                                        double* knots_y, int64_t* n_knots_host, ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE(n >= 1 && n < 2147483647ll, "ccal_isotonic_fit_binary: n must be in [1, 2^31) (got %lld)", (long long)n);
+  CCAL_REQUIRE(x && y && knots_x && knots_y && n_knots_host, "ccal_isotonic_fit_binary: NULL pointer");
+  const int ni = (int)n;
+
+  // ---- workspace layout
+  size_t sort_bytes = 0, scan_bytes = 0, select_bytes = 0;
+  CCAL_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const double*)nullptr, (double*)nullptr,
+                                               (const unsigned char*)nullptr, (unsigned char*)nullptr, ni, 0, 64, stream));
+  CCAL_CUDA_OK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, ni, stream));
+  CCAL_CUDA_OK(cub::DeviceSelect::Flagged(nullptr, select_bytes, (const double*)nullptr, (const unsigned char*)nullptr,
+                                          (double*)nullptr, (int*)nullptr, ni, stream));
+  const size_t temp_bytes = std::max(sort_bytes, std::max(scan_bytes, select_bytes));
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t sz_d = up(sizeof(double) * n), sz_u8 = up(n), sz_i = up(sizeof(int) * n), sz_u64 = up(8 * (size_t)n);
+  // xs, ux, fy | ys, keep | flag, gid, start0, start1 | ones0, cnt0, ones1, cnt1 | small | cub temp
+  const size_t total = 3 * sz_d + 2 * sz_u8 + 4 * sz_i + 4 * sz_u64 + 256 + up(temp_bytes);
+  AsyncWorkspace ws;
+  CCAL_CUDA_OK(ws.alloc(total, stream));
+  unsigned char* p = ws.ptr;
+  auto take = [&](size_t b) { unsigned char* r = p; p += b; return r; };
+  double* xs = (double*)take(sz_d); double* ux = (double*)take(sz_d); double* fy = (double*)take(sz_d);
+  unsigned char* ys = take(sz_u8); unsigned char* keep = take(sz_u8);
+  int* flag = (int*)take(sz_i); int* gid = (int*)take(sz_i);
+  int* start[2] = {(int*)take(sz_i), (int*)take(sz_i)};
+  unsigned long long* ones[2]; unsigned long long* cnt[2];
+  ones[0] = (unsigned long long*)take(sz_u64); cnt[0] = (unsigned long long*)take(sz_u64);
+  ones[1] = (unsigned long long*)take(sz_u64); cnt[1] = (unsigned long long*)take(sz_u64);
+  int* small = (int*)take(256);                 // [0] any_violation, [1] number selected
+  void* temp = take(up(temp_bytes));
+
+  // ---- sort by x, merge equal x into groups (ones, count)
+  size_t tb = temp_bytes;
+  CCAL_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, tb, x, xs, y, ys, ni, 0, 64, stream));
+  note_launch();
+  iso_unique_flags_kernel<<<iso_grid(n), kIsoThreads, 0, stream>>>(xs, n, flag);
+  note_launch();
+  tb = temp_bytes;
+  CCAL_CUDA_OK(cub::DeviceScan::InclusiveSum(temp, tb, flag, gid, ni, stream));
+  note_launch();
+  CCAL_CUDA_OK(cudaMemsetAsync(ones[0], 0, 8 * (size_t)n, stream));
+  CCAL_CUDA_OK(cudaMemsetAsync(cnt[0], 0, 8 * (size_t)n, stream));
+  iso_group_kernel<<<iso_grid(n), kIsoThreads, 0, stream>>>(xs, ys, flag, gid, n, ux, ones[0], cnt[0], start[0]);
+  note_launch();
+  int n_groups = 0;
+  CCAL_CUDA_OK(cudaMemcpyAsync(&n_groups, gid + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CCAL_CUDA_OK(cudaStreamSynchronize(stream));
+
+  // ---- pool adjacent violators in rounds
+  int nb = n_groups, cur = 0;
+  int* head = flag;            // reused
+  int* bid = gid;
+  for (int round = 0; nb > 1; ++round) {
+    CCAL_REQUIRE(round < 100000, "ccal_isotonic_fit_binary: pooling did not converge");
+    CCAL_CUDA_OK(cudaMemsetAsync(small, 0, sizeof(int), stream));
+    iso_heads_kernel<<<(nb + kIsoThreads - 1) / kIsoThreads, kIsoThreads, 0, stream>>>(ones[cur], cnt[cur], nb, head, small);
+    note_launch();
+    tb = temp_bytes;
+    CCAL_CUDA_OK(cub::DeviceScan::InclusiveSum(temp, tb, head, bid, nb, stream));
+    note_launch();
+    HostPair hp;
+    CCAL_CUDA_OK(cudaMemcpyAsync(&hp.any_violation, small, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CCAL_CUDA_OK(cudaMemcpyAsync(&hp.last_bid, bid + (nb - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CCAL_CUDA_OK(cudaStreamSynchronize(stream));
+    if (!hp.any_violation) break;
+    const int nxt = cur ^ 1;
+    CCAL_CUDA_OK(cudaMemsetAsync(ones[nxt], 0, 8 * (size_t)hp.last_bid, stream));
+    CCAL_CUDA_OK(cudaMemsetAsync(cnt[nxt], 0, 8 * (size_t)hp.last_bid, stream));
+    iso_pool_kernel<<<(nb + kIsoThreads - 1) / kIsoThreads, kIsoThreads, 0, stream>>>(ones[cur], cnt[cur], start[cur], head, bid, nb,
+                                                                                    ones[nxt], cnt[nxt], start[nxt]);
+    note_launch();
+    nb = hp.last_bid;
+    cur = nxt;
+  }
+
+  // ---- fitted value per unique x, then drop interior points of constant stretches
+  iso_expand_kernel<<<(n_groups + kIsoThreads - 1) / kIsoThreads, kIsoThreads, 0, stream>>>(ones[cur], cnt[cur], start[cur], nb,
+                                                                                           n_groups, fy);
+  note_launch();
+  iso_keep_kernel<<<(n_groups + kIsoThreads - 1) / kIsoThreads, kIsoThreads, 0, stream>>>(fy, n_groups, keep);
+  note_launch();
+  tb = temp_bytes;
+  CCAL_CUDA_OK(cub::DeviceSelect::Flagged(temp, tb, ux, keep, knots_x, small + 1, n_groups, stream));
+  note_launch();
+  tb = temp_bytes;
+  CCAL_CUDA_OK(cub::DeviceSelect::Flagged(temp, tb, fy, keep, knots_y, small + 1, n_groups, stream));
+  note_launch();
+  int n_knots = 0;
+  CCAL_CUDA_OK(cudaMemcpyAsync(&n_knots, small + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CCAL_CUDA_OK(cudaStreamSynchronize(stream));
+  CCAL_CUDA_OK(cudaGetLastError());
+  *n_knots_host = n_knots;
+  return CCAL_OK;
+}
+
+extern "C" int ccal_isotonic_transform(const double* knots_x, const double* knots_y, int64_t n_knots, const double* t,
+                                       int64_t n, double residual_scale, double* out, ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE(n_knots >= 1 && n_knots < 2147483647ll, "ccal_isotonic_transform: n_knots out of range (got %lld)", (long long)n_knots);
+  CCAL_REQUIRE(n >= 0, "ccal_isotonic_transform: negative n");
+  if (n == 0) return CCAL_OK;
+  CCAL_REQUIRE(knots_x && knots_y && t && out, "ccal_isotonic_transform: NULL pointer");
+  const long long grid = std::min<long long>((n + kIsoThreads - 1) / kIsoThreads, (long long)num_sms() * 16);
+  iso_transform_kernel<<<(int)grid, kIsoThreads, 0, stream>>>(knots_x, knots_y, (int)n_knots, t, n, residual_scale, out);
+  note_launch();
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}

@@ -283,6 +283,66 @@ def density_ratio_apply(probs: torch.Tensor, pdf_true: torch.Tensor, pdf_false: 
 
 
 # --------------------------------------------------------------------------------------
+# f-4  isotonic-regression calibrator
+# --------------------------------------------------------------------------------------
+def exp_normalise_rows(values: torch.Tensor, labels: Optional[torch.Tensor] = None):
+    """float64 exp(v) / sum(exp(v)) per row (no max shift) of an [N, C] fp32/fp64 matrix; with labels [N] also the
+    one-hot matrix (uint8 [N, C])."""
+    lib = _lib.load()
+    values = _need_cuda("values", values, (torch.float32, torch.float64), 2)
+    n, c = values.shape
+    out = torch.empty((n, c), dtype=torch.float64, device=values.device)
+    onehot = None
+    if labels is not None:
+        labels = _need_cuda("labels", labels, torch.int64, 1)
+        if labels.shape[0] != n:
+            raise ValueError("exp_normalise_rows: one label per row is required")
+        onehot = torch.empty((n, c), dtype=torch.uint8, device=values.device)
+    f32 = values.dtype == torch.float32
+    with torch.cuda.device(values.device):
+        rc = lib.ccal_exp_normalise_rows(_ptr(values) if f32 else None, None if f32 else _ptr(values), n, c, _ptr(out),
+                                         _ptr(labels), _ptr(onehot), _stream())
+    _lib.check(rc, "ccal_exp_normalise_rows")
+    return out, onehot
+
+
+def isotonic_fit_binary(x: torch.Tensor, y: torch.Tensor):
+    """scikit-learn's isotonic fit of 0/1 targets y (uint8) at x (float64), both flat CUDA tensors ->
+    (X_thresholds_, y_thresholds_) as float64 CUDA tensors.  Synchronises."""
+    import ctypes
+    lib = _lib.load()
+    x = _need_cuda("x", x.reshape(-1), torch.float64, 1)
+    y = _need_cuda("y", y.reshape(-1), torch.uint8, 1)
+    if x.shape != y.shape or x.numel() == 0:
+        raise ValueError("isotonic_fit_binary: x and y must be equally long and non-empty")
+    n = x.numel()
+    kx = torch.empty(n, dtype=torch.float64, device=x.device)
+    ky = torch.empty(n, dtype=torch.float64, device=x.device)
+    nk = ctypes.c_int64(0)
+    with torch.cuda.device(x.device):
+        rc = lib.ccal_isotonic_fit_binary(_ptr(x), _ptr(y), n, _ptr(kx), _ptr(ky), ctypes.byref(nk), _stream())
+    _lib.check(rc, "ccal_isotonic_fit_binary")
+    return kx[: nk.value].clone(), ky[: nk.value].clone()
+
+
+def isotonic_transform(knots_x: torch.Tensor, knots_y: torch.Tensor, t: torch.Tensor,
+                       residual_scale: float = 0.0) -> torch.Tensor:
+    """f(clip(t)) + residual_scale * t, f = linear interpolation between the knots; same shape as t (float64)."""
+    lib = _lib.load()
+    knots_x = _need_cuda("knots_x", knots_x, torch.float64, 1)
+    knots_y = _need_cuda("knots_y", knots_y, torch.float64, 1)
+    if knots_x.shape != knots_y.shape or knots_x.numel() == 0:
+        raise ValueError("isotonic_transform: knots_x / knots_y must be equally long and non-empty")
+    t = _need_cuda("t", t, torch.float64)
+    out = torch.empty_like(t)
+    with torch.cuda.device(t.device):
+        rc = lib.ccal_isotonic_transform(_ptr(knots_x), _ptr(knots_y), knots_x.numel(), _ptr(t), t.numel(),
+                                         float(residual_scale), _ptr(out), _stream())
+    _lib.check(rc, "ccal_isotonic_transform")
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # K3  bin statistics and exact order statistics
 # --------------------------------------------------------------------------------------
 def bin_stats(conf: torch.Tensor, pred: torch.Tensor, gt: torch.Tensor, thresholds: Sequence[float],

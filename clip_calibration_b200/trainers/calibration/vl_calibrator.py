@@ -1,11 +1,12 @@
 """Drop-in for the DAC + softmax branch of the reference's trainers/calibration/vl_calibrator.py
 (`VLCalibration.__init__ / fit / predict / build_dac_calibrator`, reference :30-109, :155-180).
 
-In scope: DAC (dac_flag) followed by softmax, and the `scaling_based` base calibrator with
-`procal_flag` = DensityRatioCalibration (reference :116-119, :95-96; CUDA KDE, see
-density_ratio_calibration.py).  The `bin_based` base calibrators (reference :121-148; netcal
-HistogramBinning / IsotonicRegression and sklearn isotonic regression, CPU statistics libraries)
-are out of scope: requesting one raises NotImplementedError instead of silently skipping it.
+In scope: DAC (dac_flag) followed by softmax; the `scaling_based` base calibrator with `procal_flag` =
+DensityRatioCalibration (reference :116-119, :95-96; CUDA KDE, density_ratio_calibration.py); the `bin_based`
+base calibrator 'multi_isotonic_regression', plain or proximity-binned through BinMeanShift (reference :133-134,
+:146-148, :97-102; GPU isotonic fit, multi_isotonic_regression.py / multi_proximity_isotonic.py).  The two netcal
+calibrators ('histogram_binning', 'isotonic_regression'; netcal is unpinned and not installed) are out of scope:
+requesting one raises NotImplementedError instead of silently skipping it.
 
 `predict(logits, proximity)` keeps the reference contract and returns probabilities [N, C].
 `predict_confidence` / `predict_from_features` are the additive routes that return only
@@ -19,16 +20,16 @@ import torch
 from ... import native
 from .density_ratio_calibration import DensityRatioCalibration
 from .distanse_aware_calibration import DistanseAwareCalibration
+from .multi_isotonic_regression import MultiIsotonicRegression
+from .multi_proximity_isotonic import BinMeanShift
 
 
 class VLCalibration():
 
     def __init__(self, cfg, base_calibration_mode=None, base_bin_calibrator_name=None, dac_flag=False,
                  procal_flag=False, val_dict=None, text_feature_dict=None):
-        if base_calibration_mode not in (None, "scaling_based"):
-            raise NotImplementedError(
-                "bin_based base calibrators (netcal / sklearn isotonic regression in the reference) are outside "
-                "the accelerated path; use the reference's VLCalibration for them")
+        if base_calibration_mode not in (None, "scaling_based", "bin_based"):
+            raise ValueError(f"unknown base_calibration_mode {base_calibration_mode!r}")
         self.cfg = cfg
         self.base_calibration_mode = base_calibration_mode
         self.base_bin_calibrator_name = base_bin_calibrator_name
@@ -54,17 +55,41 @@ class VLCalibration():
     def build_base_calibrator(self, base_bin_calibrator_name, val_image_proximity):
         """reference :112-150, `scaling_based` branch: the density-ratio calibrator is fitted on the validation
         (calibration) set - softmax of the un-scaled validation logits (:59-60), their argmax, labels, proximity."""
+        if self.base_calibration_mode == "bin_based":
+            if base_bin_calibrator_name != "multi_isotonic_regression":
+                raise NotImplementedError(
+                    f"bin calibrator {base_bin_calibrator_name!r}: the netcal calibrators (histogram_binning, "
+                    "isotonic_regression) are outside the accelerated path; use the reference's VLCalibration for them")
+            val_probs, _, _ = self._val_probs()
+            labels = self._val_labels()
+            if self.procal_flag:
+                base_calibrator = BinMeanShift("multi_isotonic_regression", MultiIsotonicRegression,
+                                               bin_strategy="quantile", normalize_conf=False, proximity_bin=5)
+                base_calibrator.fit_transform(val_probs, val_image_proximity, labels)
+            else:
+                base_calibrator = MultiIsotonicRegression()
+                base_calibrator.fit_transform(val_probs, labels)
+            return base_calibrator
         if not (self.base_calibration_mode == "scaling_based" and self.procal_flag):
             return None                             # the reference builds nothing in this case either
-        val_logits = self.val_dict["val_logits"]
-        x = val_logits.detach() if isinstance(val_logits, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(val_logits))
-        val_probs = x.to(device="cuda", dtype=torch.float32, copy=True).contiguous()
-        val_preds, _ = native.dac_softmax_logits_(val_probs, None)
-        labels = self.val_dict["val_labels"]
-        labels = labels.cpu().numpy() if isinstance(labels, torch.Tensor) else np.asarray(labels)
+        val_probs, val_preds, _ = self._val_probs()
+        labels = self._val_labels().cpu().numpy()
         base_calibrator = DensityRatioCalibration()
         base_calibrator.fit(val_probs, val_preds.cpu().numpy(), labels, val_image_proximity)
         return base_calibrator
+
+    def _val_probs(self):
+        """softmax of the un-scaled validation logits (reference :59-60) as a float32 CUDA matrix, with argmax / max."""
+        val_logits = self.val_dict["val_logits"]
+        x = val_logits.detach() if isinstance(val_logits, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(val_logits))
+        val_probs = x.to(device="cuda", dtype=torch.float32, copy=True).contiguous()
+        pred, conf = native.dac_softmax_logits_(val_probs, None)
+        return val_probs, pred, conf
+
+    def _val_labels(self) -> torch.Tensor:
+        labels = self.val_dict["val_labels"]
+        t = labels if isinstance(labels, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(labels))
+        return t.to(torch.int64)
 
     def build_dac_calibrator(self, text_feature_dict, k_dac):
         dac_calibrator = DistanseAwareCalibration()
@@ -85,9 +110,14 @@ class VLCalibration():
         work = x.to(device="cuda", dtype=torch.float32, copy=True).contiguous()
         cc = self.dac_calibrator._cc() if self.dac_calibrator is not None else None
         native.dac_softmax_logits_(work, cc)
-        if self.base_calibrator is not None:          # scaling_based + proximity: float64 [N, C] like the reference
-            prox = test_proximity if isinstance(test_proximity, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(test_proximity))
-            work, _, _ = self.base_calibrator.predict_device(work, prox.cuda())
+        if self.base_calibrator is not None:          # float64 [N, C] like the reference
+            if self.base_calibration_mode == "scaling_based":
+                prox = test_proximity if isinstance(test_proximity, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(test_proximity))
+                work, _, _ = self.base_calibrator.predict_device(work, prox.cuda())
+            elif self.procal_flag:
+                work = self.base_calibrator.transform(work, test_proximity)
+            else:
+                work = self.base_calibrator.transform(work)
         return work.cpu().numpy() if as_numpy else work
 
     # ------------------------------------------------------------------ additive

@@ -188,6 +188,24 @@ CCAL_API int ccal_density_ratio_apply(const float* probs_f32, const double* prob
                              const double* pdf_true, const double* pdf_false, double false_true_ratio,
                              double* probs_out, double* conf_cal_out, int32_t* pred_out, ccal_stream_t stream);
 
+/* ---- multi-class isotonic-regression calibrator -------------------------------------------
+ * Reference: trainers/calibration/multi_isotonic_regression.py:14-35 (scikit-learn IsotonicRegression(out_of_bounds=
+ * 'clip') on the flattened probabilities against the flattened one-hot labels) and BinMeanShift,
+ * multi_proximity_isotonic.py:130-247.
+ * ccal_exp_normalise_rows: out[i,:] = exp(v[i,:]) / sum_j exp(v[i,j]) in float64 without a max shift (:26, :33); v is
+ *   fp32 or fp64 (exactly one pointer non-NULL); with labels [n] int64, onehot_out [n,c] uint8 gets (labels[i] == j).
+ * ccal_isotonic_fit_binary: scikit-learn's fit for 0/1 targets y [n] uint8 at points x [n] float64: knots_x / knots_y
+ *   (device, capacity n) receive X_thresholds_ / y_thresholds_, *n_knots_host their number.  SYNCHRONISES the stream.
+ * ccal_isotonic_transform: out[i] = f(clip(t[i], knots_x[0], knots_x[n_knots-1])) + residual_scale * t[i], f = linear
+ *   interpolation between the knots (constant for a single knot); the reference uses residual_scale = 1e-9.
+ */
+CCAL_API int ccal_exp_normalise_rows(const float* v_f32, const double* v_f64, int64_t n, int c, double* out,
+                            const int64_t* labels, unsigned char* onehot_out, ccal_stream_t stream);
+CCAL_API int ccal_isotonic_fit_binary(const double* x, const unsigned char* y, int64_t n, double* knots_x,
+                             double* knots_y, int64_t* n_knots_host, ccal_stream_t stream);
+CCAL_API int ccal_isotonic_transform(const double* knots_x, const double* knots_y, int64_t n_knots, const double* t,
+                            int64_t n, double residual_scale, double* out, ccal_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

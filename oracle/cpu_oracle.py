@@ -336,3 +336,65 @@ def density_ratio_predict(state, probs, proximities):
     out = rest * ((1 - cal) / rest.sum(axis=-1))[:, np.newaxis]
     out[np.arange(probs.shape[0]), preds] = cal
     return out, cal
+
+
+# --------------------------------------------------------------------------------------
+# f-4  multi-class isotonic regression and its proximity-binned wrapper
+# --------------------------------------------------------------------------------------
+def multi_isotonic_fit_transform(logit, label):
+    """trainers/calibration/multi_isotonic_regression.py:14-30 (MultiIsotonicRegression.fit_transform): softmax
+    WITHOUT max shift of whatever is passed as `logit` (the caller passes probabilities), one-hot labels, scikit-learn
+    IsotonicRegression(out_of_bounds='clip') on the flattened arrays, `+ 1e-9 * p`.  Returns (p_out, calibrator).
+    scikit-learn is the reference's own dependency for this step, so the oracle calls it like the reference does."""
+    from sklearn.isotonic import IsotonicRegression
+    logit = np.asarray(logit)
+    label = np.asarray(label)
+    n_classes = logit.shape[1]
+    if label.ndim == 1:
+        onehot = np.zeros((len(label), n_classes))
+        onehot[np.arange(len(label)), label] = 1          # == label_binarize(label, classes=arange(C)) for C > 2
+        label = onehot
+    p = np.exp(logit) / np.sum(np.exp(logit), 1)[:, None]
+    calibrator = IsotonicRegression(out_of_bounds="clip")
+    y_ = calibrator.fit_transform(p.flatten(), label.flatten())
+    return y_.reshape(logit.shape) + 1e-9 * p, calibrator
+
+
+def multi_isotonic_transform(calibrator, logit):
+    """multi_isotonic_regression.py:32-35."""
+    logit = np.asarray(logit)
+    p = np.exp(logit) / np.sum(np.exp(logit), 1)[:, None]
+    return calibrator.predict(p.flatten()).reshape(logit.shape) + 1e-9 * p
+
+
+def bin_mean_shift_fit_transform(logit, proximity, label, proximity_bin: int = 5, bin_strategy: str = "quantile"):
+    """trainers/calibration/multi_proximity_isotonic.py:198-229 (BinMeanShift.fit_transform with the
+    'multi_isotonic_regression' method, normalize_conf=False): proximity bins by np.percentile edges (:158-160) or
+    uniform edges (:174-176), one MultiIsotonicRegression per bin.  Returns (probs, (edges, calibrators))."""
+    logit, proximity, label = np.asarray(logit), np.asarray(proximity), np.asarray(label)
+    if bin_strategy == "quantile":
+        edges = np.asarray(np.percentile(proximity, np.linspace(0, 100, proximity_bin + 1)))
+    else:
+        edges = np.linspace(proximity.min(), proximity.max(), proximity_bin + 1)
+    bin_no = np.searchsorted(edges[1:-1], proximity, side="right")
+    out = np.empty(logit.shape, np.float64)
+    cals = []
+    for b in range(proximity_bin):
+        idx = np.nonzero(bin_no == b)[0]
+        res, cal = multi_isotonic_fit_transform(logit[idx], label[idx])
+        out[idx] = res
+        cals.append(cal)
+    return out, (edges, cals)
+
+
+def bin_mean_shift_transform(state, logit, proximity):
+    """multi_proximity_isotonic.py:231-247."""
+    edges, cals = state
+    logit, proximity = np.asarray(logit), np.asarray(proximity)
+    bin_no = np.searchsorted(edges[1:-1], proximity, side="right")
+    out = np.empty(logit.shape, np.float64)
+    for b in range(len(cals)):
+        idx = np.nonzero(bin_no == b)[0]
+        if len(idx):
+            out[idx] = multi_isotonic_transform(cals[b], logit[idx])
+    return out

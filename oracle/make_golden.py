@@ -11,6 +11,7 @@ Reference entry points executed unmodified:
   trainers/calibration/proximity.py   get_knn_dists, get_val_image_knn_dists (.to('cuda') patched)
   trainers/calibration/density_ratio_calibration.py  DensityRatioCalibration.fit/.predict (statsmodels stubbed
       with the oracle's restatement of KDEMultivariate - the package is not installed)
+  trainers/calibration/multi_isotonic_regression.py MultiIsotonicRegression, multi_proximity_isotonic.py BinMeanShift
 and the glue the reference performs inline: `(s*img)@txt.T` in fp32 torch
 (trainers/classification/zsclip.py:97-102), scipy.special.softmax(axis=-1)
 (trainers/calibration/vl_calibrator.py:91), argmax + gather (evaluators/vl_evaluator.py:68,:83).
@@ -220,12 +221,44 @@ def density_ratio():
     np.savez_compressed(os.path.join(OUT, "density_ratio.npz"), **out)
 
 
+def isotonic():
+    """trainers/calibration/multi_isotonic_regression.py MultiIsotonicRegression and
+    trainers/calibration/multi_proximity_isotonic.py BinMeanShift('multi_isotonic_regression', ..., 'quantile',
+    proximity_bin=5) - the calls of vl_calibrator.py:133-134, :146-148 - run unmodified on the density-ratio case's
+    probabilities (the caller passes probabilities where the class says `logit`)."""
+    from trainers.calibration.multi_isotonic_regression import MultiIsotonicRegression
+    from trainers.calibration.multi_proximity_isotonic import BinMeanShift
+    g = np.load(os.path.join(OUT, "density_ratio.npz"))
+    vp, tp = g["val_probs"].astype(np.float64), g["test_probs"].astype(np.float64)
+    vl, vprox, tprox = g["val_labels"], g["val_prox"], g["test_prox"]
+    ref = MultiIsotonicRegression()
+    val_out = ref.fit_transform(vp, vl)
+    test_out = ref.transform(tp)
+    mine_val, cal = orc.multi_isotonic_fit_transform(vp, vl)
+    assert np.array_equal(mine_val, val_out) and np.array_equal(orc.multi_isotonic_transform(cal, tp), test_out)
+    rv, rt = np.arange(0, len(vp), 5), np.arange(0, len(tp), 4)        # stored row subsets keep the fixture small
+    out = {"rows_val": rv, "rows_test": rt, "val_out": val_out[rv], "test_out": test_out[rt],
+           "x_thresholds": ref.calibrator.X_thresholds_, "y_thresholds": ref.calibrator.y_thresholds_}
+    for strategy in ("quantile", "uniform"):
+        bms = BinMeanShift("multi_isotonic_regression", MultiIsotonicRegression, bin_strategy=strategy,
+                           normalize_conf=False, proximity_bin=5)
+        b_val = bms.fit_transform(vp, vprox, vl)
+        b_test = bms.transform(tp, tprox)
+        m_val, state = orc.bin_mean_shift_fit_transform(vp, vprox, vl, 5, strategy)
+        assert np.array_equal(m_val, b_val) and np.array_equal(orc.bin_mean_shift_transform(state, tp, tprox), b_test)
+        out[f"bms_{strategy}_edges"] = np.asarray(bms.bin_edges, dtype=np.float64)
+        out[f"bms_{strategy}_val_out"], out[f"bms_{strategy}_test_out"] = b_val[rv], b_test[rt]
+    print("isotonic: %d knots; BinMeanShift quantile edges %s" % (len(out["x_thresholds"]), np.round(out["bms_quantile_edges"], 5)))
+    np.savez_compressed(os.path.join(OUT, "isotonic.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     metric_edge_cases()
     proximity_and_piece()
     density_ratio()
+    isotonic()
     run_case("eurosat")
     run_case("sun397_l14", ks=(1, 5, 10))
     run_case("imagenet")

@@ -511,7 +511,7 @@ def test_vl_calibration_scaling_based_with_proximity(cuda_lib, golden):
     assert out.dtype == np.float64
     np.testing.assert_allclose(out, g["f32_probs_out"], rtol=5e-5, atol=1e-12)   # probabilities re-derived through log/softmax in fp32
     with pytest.raises(NotImplementedError):
-        vl_calibrator.VLCalibration(None, base_calibration_mode="bin_based", val_dict=val_dict)
+        vl_calibrator.VLCalibration(None, base_calibration_mode="bin_based", val_dict=val_dict).fit()   # netcal default
 
 
 # ----------------------------------------------------------------------------- macro-F1 (evaluator)
@@ -588,3 +588,83 @@ def test_scorer_evaluate_reports_every_reference_key(cuda_lib, golden):
     assert abs(res["ace"] - 100.0 * float(g["dac_ace10"])) < 1e-3
     with pytest.raises(RuntimeError):
         pipeline.CalibratedScorer(case.txt_tuned, None, group=False).evaluate()
+
+
+# ----------------------------------------------------------------------------- f-4 isotonic calibrators
+def test_multi_isotonic_regression_matches_reference_fixture(cuda_lib, golden):
+    from clip_calibration_b200.trainers.calibration.multi_isotonic_regression import MultiIsotonicRegression
+    g, d = golden("isotonic"), golden("density_ratio")
+    vp, tp = d["val_probs"].astype(np.float64), d["test_probs"].astype(np.float64)
+    cal = MultiIsotonicRegression()
+    val_out = cal.fit_transform(vp, d["val_labels"])
+    assert val_out.dtype == np.float64 and val_out.shape == vp.shape
+    # knots = scikit-learn's X_thresholds_ / y_thresholds_: exact integer pooling -> same knots, values to an ulp
+    np.testing.assert_allclose(cal.calibrator.X_thresholds_, g["x_thresholds"], rtol=1e-15, atol=0)
+    np.testing.assert_allclose(cal.calibrator.y_thresholds_, g["y_thresholds"], rtol=1e-13, atol=1e-16)
+    # outputs: exp() differs by an ulp between CUDA and numpy; a steep segment of the fit amplifies that
+    np.testing.assert_allclose(val_out[g["rows_val"]], g["val_out"], rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(cal.transform(tp)[g["rows_test"]], g["test_out"], rtol=1e-8, atol=1e-12)
+    # one-hot label matrix instead of class indices
+    onehot = (d["val_labels"][:, None] == np.arange(vp.shape[1])[None]).astype(np.float64)
+    cal2 = MultiIsotonicRegression()
+    np.testing.assert_allclose(cal2.fit_transform(vp, onehot), val_out, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("n,c,seed", [(1, 2, 0), (50, 3, 1), (400, 10, 2), (3000, 100, 3), (20000, 120, 4)])
+def test_isotonic_fit_against_sklearn(cuda_lib, n, c, seed):
+    """ccal_isotonic_fit_binary + ccal_isotonic_transform against scikit-learn on random problems with many exact
+    duplicates (quantised x), all-equal targets and a single sample."""
+    from sklearn.isotonic import IsotonicRegression
+    rng = np.random.default_rng(seed)
+    x = rng.random(n * c)
+    if seed % 2 == 0:
+        x = np.round(x * 50) / 50                                       # heavy ties in x
+    y = (rng.random(n * c) < x).astype(np.uint8) if seed != 1 else np.ones(n * c, np.uint8)
+    iso = IsotonicRegression(out_of_bounds="clip").fit(x, y.astype(np.float64))
+    kx, ky = native.isotonic_fit_binary(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())
+    np.testing.assert_allclose(kx.cpu().numpy(), iso.X_thresholds_, rtol=0, atol=0)
+    np.testing.assert_allclose(ky.cpu().numpy(), iso.y_thresholds_, rtol=1e-13, atol=1e-16)
+    t = np.concatenate([rng.random(1000) * 1.4 - 0.2, x[:100]])        # includes out-of-range points (clipped)
+    got = native.isotonic_transform(kx, ky, torch.from_numpy(t).cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, iso.predict(t), rtol=1e-12, atol=1e-15)
+
+
+def test_bin_mean_shift_matches_reference_fixture(cuda_lib, golden):
+    from clip_calibration_b200.trainers.calibration.multi_isotonic_regression import MultiIsotonicRegression
+    from clip_calibration_b200.trainers.calibration.multi_proximity_isotonic import BinMeanShift
+    g, d = golden("isotonic"), golden("density_ratio")
+    vp, tp = d["val_probs"].astype(np.float64), d["test_probs"].astype(np.float64)
+    for strategy in ("quantile", "uniform"):
+        bms = BinMeanShift("multi_isotonic_regression", MultiIsotonicRegression, bin_strategy=strategy,
+                           normalize_conf=False, proximity_bin=5)
+        val_out = bms.fit_transform(vp, d["val_prox"], d["val_labels"])
+        np.testing.assert_allclose(bms.bin_edges, g[f"bms_{strategy}_edges"], rtol=1e-7)     # float32 proximities
+        np.testing.assert_allclose(val_out[g["rows_val"]], g[f"bms_{strategy}_val_out"], rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(bms.transform(tp, d["test_prox"])[g["rows_test"]], g[f"bms_{strategy}_test_out"],
+                                   rtol=1e-8, atol=1e-12)
+    with pytest.raises(NotImplementedError):
+        BinMeanShift("histogram_binning", MultiIsotonicRegression)
+
+
+def test_vl_calibration_bin_based_multi_isotonic(cuda_lib, golden):
+    """VLCalibration(base_calibration_mode='bin_based', base_bin_calibrator_name='multi_isotonic_regression') with and
+    without proximity (reference vl_calibrator.py:97-102, :133-134, :146-148)."""
+    g, d = golden("isotonic"), golden("density_ratio")
+    val_logits = np.log(d["val_probs"].astype(np.float64))
+    test_logits = np.log(d["test_probs"].astype(np.float64))
+    val_dict = {"val_logits": val_logits, "val_labels": d["val_labels"], "val_image_features": None,
+                "val_text_features": None, "val_image_knn_dists": -np.log(d["val_prox"].astype(np.float64))[:, None]}
+    for procal, key in ((False, "test_out"), (True, "bms_quantile_test_out")):
+        cal = vl_calibrator.VLCalibration(None, base_calibration_mode="bin_based",
+                                          base_bin_calibrator_name="multi_isotonic_regression", procal_flag=procal,
+                                          val_dict=val_dict)
+        cal.fit()
+        out = cal.predict(test_logits, d["test_prox"])
+        assert out.dtype == np.float64
+        # probabilities re-derived through log / fp32 softmax: knots and inputs move by ~1e-7, outputs stay close
+        # except where a point crosses a step of the fitted function
+        diff = np.abs(out[g["rows_test"]] - g[key])
+        assert np.quantile(diff, 0.99) < 1e-4 and diff.mean() < 1e-4
+    with pytest.raises(NotImplementedError):
+        vl_calibrator.VLCalibration(None, base_calibration_mode="bin_based", base_bin_calibrator_name="histogram_binning",
+                                    val_dict=val_dict).fit()

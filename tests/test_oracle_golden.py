@@ -89,3 +89,20 @@ def test_density_ratio_matches_reference(golden):
     state64 = orc.density_ratio_fit(g["val_probs"].astype(np.float64), g["val_preds"], g["val_labels"], g["val_prox"])
     _, cal64 = orc.density_ratio_predict(state64, g["test_probs"].astype(np.float64), g["test_prox"])
     np.testing.assert_allclose(cal64, g["f64_conf_cal"], rtol=1e-12, atol=0)
+
+
+def test_isotonic_calibrators_match_reference(golden):
+    """MultiIsotonicRegression / BinMeanShift outputs recorded from the reference classes (oracle/make_golden.py)."""
+    g, d = golden("isotonic"), golden("density_ratio")
+    vp, tp = d["val_probs"].astype(np.float64), d["test_probs"].astype(np.float64)
+    rv, rt = g["rows_val"], g["rows_test"]
+    val_out, cal = orc.multi_isotonic_fit_transform(vp, d["val_labels"])
+    np.testing.assert_allclose(val_out[rv], g["val_out"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(orc.multi_isotonic_transform(cal, tp)[rt], g["test_out"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(cal.X_thresholds_, g["x_thresholds"], rtol=0, atol=0)
+    for strategy in ("quantile", "uniform"):
+        b_val, state = orc.bin_mean_shift_fit_transform(vp, d["val_prox"], d["val_labels"], 5, strategy)
+        np.testing.assert_allclose(state[0], g[f"bms_{strategy}_edges"], rtol=1e-15)
+        np.testing.assert_allclose(b_val[rv], g[f"bms_{strategy}_val_out"], rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(orc.bin_mean_shift_transform(state, tp, d["test_prox"])[rt],
+                                   g[f"bms_{strategy}_test_out"], rtol=1e-13, atol=1e-15)
