@@ -47,8 +47,13 @@ exp_normalise_rows_kernel(const T* __restrict__ v, long long n, int c, double* _
     const bool live = row < n;
     const T* x = v + (live ? row : 0) * (long long)c;
     double sum = 0.0;
+    double* o = out + (live ? row : 0) * (long long)c;
     if (live)
-      for (int j = t; j < c; j += GROUP) sum += exp((double)x[j]);
+      for (int j = t; j < c; j += GROUP) {              // exp once: park it in the output row, rescale below
+        const double e = exp((double)x[j]);
+        o[j] = e;
+        sum += e;
+      }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
     if (GROUP > 32) {
@@ -60,8 +65,8 @@ exp_normalise_rows_kernel(const T* __restrict__ v, long long n, int c, double* _
     }
     if (!live) continue;
     const long long lab = labels ? labels[row] : -1;
-    for (int j = t; j < c; j += GROUP) {
-      out[row * (long long)c + j] = exp((double)x[j]) / sum;
+    for (int j = t; j < c; j += GROUP) {                // every thread re-reads only what it wrote itself
+      o[j] = o[j] / sum;
       if (onehot) onehot[row * (long long)c + j] = (unsigned char)(lab == j);
     }
   }
@@ -135,13 +140,23 @@ __global__ void iso_keep_kernel(const double* __restrict__ fy, int n_groups, uns
 }
 
 // ---------------------------------------------------------------------------------------- transform
+constexpr int kIsoSmemKnots = 3072;           // knots staged in shared memory (48 KB); more stay in global memory / L1
+
+template <bool kSmem>
 __global__ void __launch_bounds__(kIsoThreads)
-iso_transform_kernel(const double* __restrict__ kx, const double* __restrict__ ky, int nk, const double* __restrict__ t,
+iso_transform_kernel(const double* __restrict__ gx, const double* __restrict__ gy, int nk, const double* __restrict__ t,
                      long long n, double residual_scale, double* __restrict__ out) {
+  extern __shared__ double s_knots[];            // [nk] x then [nk] y
+  const double* kx = gx;
+  const double* ky = gy;
+  if (kSmem) {
+    for (int j = threadIdx.x; j < nk; j += kIsoThreads) { s_knots[j] = gx[j]; s_knots[nk + j] = gy[j]; }
+    __syncthreads();
+    kx = s_knots;
+    ky = s_knots + nk;
+  }
   const double x_min = kx[0], x_max = kx[nk - 1];
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double v = t[i];
+  auto f = [&](double v) {
     double r;
     if (nk == 1) {
       r = ky[0];
@@ -157,7 +172,17 @@ iso_transform_kernel(const double* __restrict__ kx, const double* __restrict__ k
       const double slope = (y1 - y0) / (x1 - x0);
       r = slope * (x - x0) + y0;                                   // scipy interp1d, kind='linear'
     }
-    out[i] = r + residual_scale * v;
+    return r + residual_scale * v;
+  };
+  // four independent loads in flight per thread
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < n) ? t[i + u * stride] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < n) out[i + u * stride] = f(v[u]);
   }
 }
 
@@ -296,7 +321,11 @@ extern "C" int ccal_isotonic_transform(const double* knots_x, const double* knot
   if (n == 0) return CCAL_OK;
   CCAL_REQUIRE(knots_x && knots_y && t && out, "ccal_isotonic_transform: NULL pointer");
   const long long grid = std::min<long long>((n + kIsoThreads - 1) / kIsoThreads, (long long)num_sms() * 16);
-  iso_transform_kernel<<<(int)grid, kIsoThreads, 0, stream>>>(knots_x, knots_y, (int)n_knots, t, n, residual_scale, out);
+  if (n_knots <= kIsoSmemKnots)
+    iso_transform_kernel<true><<<(int)grid, kIsoThreads, (size_t)n_knots * 16, stream>>>(knots_x, knots_y, (int)n_knots, t, n,
+                                                                                         residual_scale, out);
+  else
+    iso_transform_kernel<false><<<(int)grid, kIsoThreads, 0, stream>>>(knots_x, knots_y, (int)n_knots, t, n, residual_scale, out);
   note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
