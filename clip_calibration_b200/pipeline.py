@@ -59,16 +59,35 @@ class CalibratedScorer:
         return t.detach().to(self.device).to(self.operand_dtype).contiguous()
 
     @classmethod
-    def from_dac(cls, base_zs, cur_zs, base_tuned, cur_tuned, k: int = 5, **kw):
-        """Fit DAC on the four text matrices (this rank, redundantly) and score against the tuned
-        test-vocabulary features - what VLBaseLearner.test + build_dac_calibrator set up
-        (base_learner.py:117-119, vl_calibrator.py:155-180).  Host inputs are uploaded once."""
+    def from_dac(cls, base_zs, cur_zs, base_tuned, cur_tuned, k: int = 5, share_text: bool = False, **kw):
+        """Fit DAC on the four text matrices and score against the tuned test-vocabulary features - what
+        VLBaseLearner.test + build_dac_calibrator set up (base_learner.py:117-119, vl_calibrator.py:155-180).
+        Host inputs are uploaded once.  By default every rank does this redundantly.  With `share_text` (all ranks
+        hold the SAME text features and call together) only rank 0 of the group uploads and fits; the scoring
+        operand and the per-class multipliers reach the other ranks by NCCL broadcast over NVLink (51 MB + 0.2 MB
+        at 49,408 x 512) instead of N uploads competing for the host's memory bandwidth."""
         from .trainers.calibration.distanse_aware_calibration import DistanseAwareCalibration, _to_cuda_f32
-        cur_tuned_dev = _to_cuda_f32(cur_tuned, "current_text_features_tuned")
-        dac = DistanseAwareCalibration()
-        dac.fit(base_zs, cur_zs, base_tuned, cur_tuned_dev, k, sync_host_copy=False)
-        obj = cls(cur_tuned_dev, dac.class_confidence_device, **kw)
-        obj.dac = dac
+        group = kw.get("group")
+        shared = (share_text and group is not False and torch.distributed.is_available()
+                  and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1)
+        if shared and torch.distributed.get_rank(group) != 0:
+            rows, dim = (int(x) for x in cur_tuned.shape)
+            dev = torch.device(kw["device"]) if kw.get("device") is not None else torch.device("cuda", torch.cuda.current_device())
+            probe = cur_tuned if isinstance(cur_tuned, torch.Tensor) else torch.from_numpy(np.asarray(cur_tuned)[:1])
+            dtype = native.operand_dtype_for(probe, kw.get("operand_dtype"))
+            obj = cls(torch.empty((rows, dim), dtype=dtype, device=dev),
+                      torch.empty(rows, dtype=torch.float32, device=dev), **kw)
+            obj.dac = None
+        else:
+            cur_tuned_dev = _to_cuda_f32(cur_tuned, "current_text_features_tuned")
+            dac = DistanseAwareCalibration()
+            dac.fit(base_zs, cur_zs, base_tuned, cur_tuned_dev, k, sync_host_copy=False)
+            obj = cls(cur_tuned_dev, dac.class_confidence_device, **kw)
+            obj.dac = dac
+        if shared:
+            src = torch.distributed.get_global_rank(group, 0) if group is not None else 0
+            torch.distributed.broadcast(obj.txt, src=src, group=group)
+            torch.distributed.broadcast(obj.class_conf, src=src, group=group)
         return obj
 
     # ------------------------------------------------------------------ scoring
