@@ -10,7 +10,10 @@
  *   - every pointer is a DEVICE pointer owned by the caller unless its name ends in _host;
  *   - row-major, contiguous; feature matrices are [rows, D] with D contiguous;
  *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it, the caller
- *     synchronises;
+ *     synchronises (the one exception, ccal_isotonic_fit_binary, returns a size to the host and says so);
+ *   - scratch memory: a call that needs any takes it from the device's stream-ordered pool
+ *     (cudaMallocAsync / cudaFreeAsync on `stream`) and returns it before the call ends in stream order; the
+ *     library keeps no device state between calls (TMA descriptors are built per call) and is re-entrant;
  *   - return value 0 = OK, otherwise a CCAL_ERR_* code; ccal_last_error() gives the
  *     thread-local message.  There is no CPU fallback: a device that is not sm_100 fails.
  *   - bin tables are [(n_thr+1)][3] unsigned 64-bit {count, n_correct, sum(round(conf*2^40))},
