@@ -123,5 +123,6 @@ class DensityRatioCalibration():
               else proximities).cuda().to(torch.float64).contiguous()
         t = self.dens_true.pdf_device(qx, qy)
         f = self.dens_false.pdf_device(qx, qy)
-        cal = t / torch.clamp(t + f * float(self.false_true_ratio), min=1e-10)
+        # a one-column "probability matrix": the row kernel then only forms t / max(t + f * ratio, 1e-10)
+        _, cal, _ = native.density_ratio_apply(qx.reshape(-1, 1), t, f, float(self.false_true_ratio))
         return cal.cpu().numpy() if as_numpy else cal
