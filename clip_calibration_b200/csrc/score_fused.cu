@@ -112,6 +112,26 @@ template <bool kMasked, int kMode>
 __device__ __forceinline__ void exp_chunk(const uint32_t (&raw)[32], int nv, float a2, float b2, float& sum,
                                           float& wsum) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, w0 = 0.f, w1 = 0.f;
+  if (!kMasked && kMode == 0) {
+    // full chunk, confidence only: the scale-and-shift and the four partial sums run as packed fp32 pairs
+    // (FFMA2 / FADD2) - the same IEEE operations in the same order as the scalar code below, two per instruction
+    const unsigned long long aa = ptx::pack2(a2, a2), bb = ptx::pack2(-b2, -b2);
+    unsigned long long s01 = 0, s23 = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float x0, x1, x2, x3;
+      ptx::unpack2(ptx::fma2(ptx::pack2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1])), aa, bb), x0, x1);
+      ptx::unpack2(ptx::fma2(ptx::pack2(__uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3])), aa, bb), x2, x3);
+      const unsigned long long e01 = ptx::pack2(ptx::ex2_approx(x0), ptx::ex2_approx(x1));
+      const unsigned long long e23 = ptx::pack2(ptx::ex2_approx(x2), ptx::ex2_approx(x3));
+      s01 = j == 0 ? e01 : ptx::add2(s01, e01);          // 0 + e == e exactly (e >= +0)
+      s23 = j == 0 ? e23 : ptx::add2(s23, e23);
+    }
+    ptx::unpack2(s01, s0, s1);
+    ptx::unpack2(s23, s2, s3);
+    sum += (s0 + s1) + (s2 + s3);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     float e[4];

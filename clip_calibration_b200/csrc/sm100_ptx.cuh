@@ -220,6 +220,27 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): one instruction for two IEEE fp32 operations, element-wise identical to the
+// scalar forms.  Halves the issue slots of the softmax epilogue's scale-and-shift and of its partial sums.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // Shared-memory matrix descriptor: K-major operand tile, 128-byte swizzle, rows of 64 bf16/fp16
 // (= one 128 B swizzle span), 8-row core groups 1024 B apart.  Matches the layout TMA writes with
 // CU_TENSOR_MAP_SWIZZLE_128B and a {64, rows} box.
