@@ -112,7 +112,7 @@ template <bool kMasked, int kMode>
 __device__ __forceinline__ void exp_chunk(const uint32_t (&raw)[32], int nv, float a2, float b2, float& sum,
                                           float& wsum) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, w0 = 0.f, w1 = 0.f;
-  if (!kMasked && kMode == 0) {
+  if constexpr (!kMasked && kMode == 0) {
     // full chunk, confidence only: the scale-and-shift and the four partial sums run as packed fp32 pairs
     // (FFMA2 / FADD2) - the same IEEE operations in the same order as the scalar code below, two per instruction
     const unsigned long long aa = ptx::pack2(a2, a2), bb = ptx::pack2(-b2, -b2);
@@ -351,13 +351,25 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
         ptx::mbar_wait(&ctl->tmem_full[as], (acc_it >> 1) & 1u);
         ptx::tc_fence_after();
         const int valid = min(kBlockN, p.c - nt * kBlockN);
-        for (int ch = 0; ch * 32 < valid; ++ch) {
-          uint32_t raw[32];
-          ptx::tmem_ld_32x32(tmem_base + lane_sel + as * kBlockN + ch * 32, raw);
-          ptx::tmem_ld_wait(raw);
-          const int nv = valid - ch * 32;
-          if (nv >= 32) max_chunk<false>(raw, 32, nt * kBlockN + ch * 32, m, arg);
-          else max_chunk<true>(raw, nv, nt * kBlockN + ch * 32, m, arg);
+        if (valid == kBlockN) {
+          // full tile (all but the last one): straight-line code, no per-chunk loop or mask bookkeeping - every
+          // instruction the epilogue does not issue is power the tensor pipe keeps
+#pragma unroll
+          for (int ch = 0; ch < kBlockN / 32; ++ch) {
+            uint32_t raw[32];
+            ptx::tmem_ld_32x32(tmem_base + lane_sel + as * kBlockN + ch * 32, raw);
+            ptx::tmem_ld_wait(raw);
+            max_chunk<false>(raw, 32, nt * kBlockN + ch * 32, m, arg);
+          }
+        } else {
+          for (int ch = 0; ch * 32 < valid; ++ch) {
+            uint32_t raw[32];
+            ptx::tmem_ld_32x32(tmem_base + lane_sel + as * kBlockN + ch * 32, raw);
+            ptx::tmem_ld_wait(raw);
+            const int nv = valid - ch * 32;
+            if (nv >= 32) max_chunk<false>(raw, 32, nt * kBlockN + ch * 32, m, arg);
+            else max_chunk<true>(raw, nv, nt * kBlockN + ch * 32, m, arg);
+          }
         }
         release_acc(as);
       }
@@ -382,6 +394,15 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
         // tiles in class order.  The column-split mode stores the per-tile partials and its finish kernel adds
         // them in the same order, so confidences are bit-identical however the work was cut.
         float tile_sum = 0.f;
+        if (kMode == 0 && valid == kBlockN) {
+#pragma unroll
+          for (int ch = 0; ch < kBlockN / 32; ++ch) {
+            uint32_t raw[32];
+            ptx::tmem_ld_32x32(tmem_base + lane_sel + as * kBlockN + ch * 32, raw);
+            ptx::tmem_ld_wait(raw);
+            exp_chunk<false, kMode>(raw, 32, a2, b2, tile_sum, wsum);
+          }
+        } else
         for (int ch = 0; ch * 32 < valid; ++ch) {
           uint32_t raw[32];
           ptx::tmem_ld_32x32(tmem_base + lane_sel + as * kBlockN + ch * 32, raw);

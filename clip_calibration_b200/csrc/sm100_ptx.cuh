@@ -38,14 +38,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// try_wait may suspend the thread until the phase completes or a time limit expires; the explicit limit (ns) keeps a
+// waiting warp asleep instead of polling every few hundred cycles - on a power-capped part every issued instruction
+// of a spin loop is clock taken from the tensor pipe.
+constexpr uint32_t kSuspendHintNs = 20000;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }
@@ -54,22 +58,33 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.  The polling loop and its
+// time-out live out of line so that the inlined fast path is one try_wait and one branch.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
   uint64_t t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xFFFu) == 0) {
-      const uint64_t now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ull) {     // 4 s
-        printf("ccal: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
-               (int)threadIdx.x, smem_u32(bar), parity);
-        __trap();
-      }
+  for (;;) {
+    for (int i = 0; i < 1024; ++i) {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar_addr), "r"(parity), "r"(kSuspendHintNs)
+          : "memory");
+      if (ok) return;
+    }
+    const uint64_t now = globaltimer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000ull) {     // 4 s
+      printf("ccal: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar_addr, parity);
+      __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(smem_u32(bar), parity);
 }
 
 // ---------------------------------------------------------------- TMA
