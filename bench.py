@@ -382,7 +382,8 @@ def main():
         # side is uploaded and fitted by rank 0 and broadcast over NVLink (the text features are replicated)
         scorer = pipeline.CalibratedScorer.from_dac(host_txt["bz"], host_txt["cz"], host_txt["bt"], host_txt["ct"],
                                                     k=K_DAC, logit_scale=LOGIT_SCALE, n_bins=N_BINS,
-                                                    operand_dtype=torch.bfloat16, share_text=world > 1)
+                                                    operand_dtype=torch.bfloat16, share_text=world > 1,
+                                                    overlap_fit=world == 1)
         scorer.accumulate_host(host_img, host_labels, chunk_rows=131072)                     # chunked H2D + scoring
         e2e_table["t"] = scorer.reduced_table()                                              # all-reduce + D2H
 

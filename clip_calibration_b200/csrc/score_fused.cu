@@ -616,8 +616,11 @@ static int choose_ctas(int64_t n) {
 }
 
 // One launch over 16-bit operands.  `img_lo` / `txt_lo` != NULL selects the split-precision variant.
+// pass_sel: -1 = both passes in one launch; 0 = pass 1 only (row maximum of the raw dot products -> p.part_max,
+// first argmax -> p.part_arg); 1 = pass 2 only (reads them back through p.row_max_in / p.row_pred_in).
 static int launch_fused(int mode, const void* img, const void* txt, const void* img_lo, const void* txt_lo, int64_t n,
-                        int c, int d, int dtype, ScoreParams p, const ThrBlock& thr, cudaStream_t stream) {
+                        int c, int d, int dtype, ScoreParams p, const ThrBlock& thr, cudaStream_t stream,
+                        int pass_sel = -1) {
   const bool split = img_lo != nullptr;
   int ctas = choose_ctas(n);
   // Column-split mode: when the image rows cannot fill the SMs but the vocabulary is large, every row tile is
@@ -626,7 +629,7 @@ static int launch_fused(int mode, const void* img, const void* txt, const void* 
   const int tiles128 = (int)((n + kBlockM - 1) / kBlockM);
   const int col_tiles = (c + kBlockN - 1) / kBlockN;
   int S = 1;
-  if (mode == 0 && col_tiles >= 4 && tiles128 * 2 <= sms_all && !getenv("CCAL_SCORE_NOSPLIT")) {
+  if (mode == 0 && pass_sel < 0 && col_tiles >= 4 && tiles128 * 2 <= sms_all && !getenv("CCAL_SCORE_NOSPLIT")) {
     S = sms_all / tiles128;
     if (S > col_tiles) S = col_tiles;
     if (S > 1) ctas = 1;
@@ -664,6 +667,7 @@ static int launch_fused(int mode, const void* img, const void* txt, const void* 
   const int n_work = p.n_row_tiles * S;
   const int grid = (n_work < units ? n_work : units) * ctas;
   p.n_splits = S; p.pass_lo = 0; p.pass_hi = 1;
+  if (pass_sel >= 0) p.pass_lo = p.pass_hi = pass_sel;
   auto launch = [&](const ScoreParams& q) -> int {
 #define CCAL_LAUNCH(C, R, M, SP) \
   launch_variant<C, R, M, SP>(map_img, map_txt, map_img_lo, map_txt_lo, q, thr, grid, smem, stream)
@@ -753,7 +757,7 @@ static int grid_for_elems(long long n, int per_thread) {
 }
 
 static int run_fused(int mode, const void* img, const void* txt, int64_t n, int c, int d, int dtype, ScoreParams p,
-                     const ThrBlock& thr, cudaStream_t stream) {
+                     const ThrBlock& thr, cudaStream_t stream, int pass_sel = -1) {
   int rc = ccal_check_device();
   if (rc) return rc;
   CCAL_REQUIRE(n >= 1 && c >= 1, "fused scoring: bad shape n=%lld c=%d", (long long)n, c);
@@ -763,7 +767,8 @@ static int run_fused(int mode, const void* img, const void* txt, int64_t n, int 
   CCAL_REQUIRE(img && txt, "fused scoring: NULL feature pointer");
   CCAL_REQUIRE(((uintptr_t)img % 16 == 0) && ((uintptr_t)txt % 16 == 0), "fused scoring: 16-byte alignment required");
   CCAL_REQUIRE(n <= 2147483647ll - 2 * kBlockM, "fused scoring: n must fit int32 row coordinates");
-  if (dtype != CCAL_F32) return launch_fused(mode, img, txt, nullptr, nullptr, n, c, d, dtype, p, thr, stream);
+  if (dtype != CCAL_F32) return launch_fused(mode, img, txt, nullptr, nullptr, n, c, d, dtype, p, thr, stream, pass_sel);
+  CCAL_REQUIRE(pass_sel < 0, "the two-launch form (ccal_score_pass1 / ccal_score_pass2) takes fp16 / bf16 operands only");
 
   // ---- fp32 features: split into fp16 pairs (transient stream-ordered workspace), score chunk by chunk
   const int64_t chunk = n < 262144 ? n : 262144;
@@ -837,6 +842,48 @@ extern "C" int ccal_score_fused(const void* img, const void* txt, const float* c
   }
   CCAL_REQUIRE(logit_scale > 0.f, "ccal_score_fused: logit_scale must be positive");
   return run_fused(0, img, txt, n, c, d, dtype, p, thr, (cudaStream_t)stream);
+}
+
+extern "C" int ccal_score_pass1(const void* img, const void* txt, int64_t n, int c, int d, int dtype,
+                                float* rowdot_max_out, int32_t* pred_out, ccal_stream_t stream) {
+  if (n == 0) return CCAL_OK;
+  CCAL_REQUIRE(rowdot_max_out && pred_out, "ccal_score_pass1: NULL output");
+  ScoreParams p{};
+  ThrBlock thr{};
+  p.scale = 1.0f;
+  p.part_max = rowdot_max_out;
+  p.part_arg = pred_out;
+  return run_fused(0, img, txt, n, c, d, dtype, p, thr, (cudaStream_t)stream, 0);
+}
+
+extern "C" int ccal_score_pass2(const void* img, const void* txt, const float* class_conf, float logit_scale,
+                                int64_t n, int c, int d, int dtype, const float* rowdot_max_in, const int32_t* pred_in,
+                                float* conf_out, float* rowmax_out, const int64_t* labels,
+                                const double* thresholds_host, int n_thr, unsigned long long* table,
+                                ccal_stream_t stream) {
+  if (n == 0) return CCAL_OK;
+  CCAL_REQUIRE(rowdot_max_in && pred_in, "ccal_score_pass2: the row maxima and labels of ccal_score_pass1 are required");
+  ScoreParams p{};
+  ThrBlock thr{};
+  p.scale = logit_scale;
+  p.class_conf = class_conf;
+  p.conf_out = conf_out;
+  p.rowmax_out = rowmax_out;
+  p.row_max_in = rowdot_max_in;
+  p.row_pred_in = pred_in;
+  p.labels = reinterpret_cast<const long long*>(labels);
+  p.table = table;
+  p.n_thr = 0;
+  if (table != nullptr) {
+    CCAL_REQUIRE(labels != nullptr, "ccal_score_pass2: labels are required when a bin table is requested");
+    CCAL_REQUIRE(n_thr >= 0 && n_thr <= CCAL_MAX_THRESHOLDS, "ccal_score_pass2: n_thr out of range");
+    CCAL_REQUIRE(n_thr == 0 || thresholds_host != nullptr, "ccal_score_pass2: thresholds NULL");
+    CCAL_REQUIRE(n < (1ll << 32), "ccal_score_pass2: n must be < 2^32 per call when binning");
+    p.n_thr = n_thr;
+    for (int i = 0; i < n_thr; ++i) thr.t[i] = ceil_to_f32(thresholds_host[i]);
+  }
+  CCAL_REQUIRE(logit_scale > 0.f, "ccal_score_pass2: logit_scale must be positive");
+  return run_fused(0, img, txt, n, c, d, dtype, p, thr, (cudaStream_t)stream, 1);
 }
 
 extern "C" int ccal_ts_loss_grad(const void* img, const void* txt, const int64_t* labels, float log_scale,

@@ -109,6 +109,63 @@ def score_fused(img: torch.Tensor, txt: torch.Tensor, class_conf: Optional[torch
     return pred, conf, rowmax
 
 
+def score_pass1(img: torch.Tensor, txt: torch.Tensor):
+    """First half of score_fused: (max of the RAW dot products float32 [N], first argmax int32 [N]).  Needs no
+    multipliers, so it can run while the DAC fit is still in flight.  fp16 / bf16 operands."""
+    lib = _lib.load()
+    img = _need_cuda("img", img, (torch.bfloat16, torch.float16), 2)
+    txt = _need_cuda("txt", txt, img.dtype, 2)
+    if img.shape[1] != txt.shape[1]:
+        raise ValueError(f"feature widths differ: img {tuple(img.shape)} vs txt {tuple(txt.shape)}")
+    n, d = img.shape
+    dotmax = torch.empty(n, dtype=torch.float32, device=img.device)
+    pred = torch.empty(n, dtype=torch.int32, device=img.device)
+    if n:
+        with torch.cuda.device(img.device):
+            rc = lib.ccal_score_pass1(_ptr(img), _ptr(txt), n, txt.shape[0], d, _DTYPES[img.dtype], _ptr(dotmax),
+                                      _ptr(pred), _stream())
+        _lib.check(rc, "ccal_score_pass1")
+    return dotmax, pred
+
+
+def score_pass2(img: torch.Tensor, txt: torch.Tensor, dotmax: torch.Tensor, pred: torch.Tensor,
+                class_conf: Optional[torch.Tensor] = None, logit_scale: float = 100.0,
+                labels: Optional[torch.Tensor] = None, thresholds: Optional[Sequence[float]] = None,
+                table: Optional[torch.Tensor] = None, want_conf: bool = True):
+    """Second half of score_fused from the outputs of score_pass1: confidence float32 [N] (or None) and the
+    accumulated bin table; bit-identical to the one-launch form."""
+    lib = _lib.load()
+    img = _need_cuda("img", img, (torch.bfloat16, torch.float16), 2)
+    txt = _need_cuda("txt", txt, img.dtype, 2)
+    n, d = img.shape
+    c = txt.shape[0]
+    dotmax = _need_cuda("dotmax", dotmax, torch.float32, 1)
+    pred = _need_cuda("pred", pred, torch.int32, 1)
+    if dotmax.numel() != n or pred.numel() != n:
+        raise ValueError("dotmax / pred must hold one entry per image")
+    if class_conf is not None:
+        class_conf = _need_cuda("class_conf", class_conf, torch.float32, 1)
+        if class_conf.numel() != c:
+            raise ValueError(f"class_conf has {class_conf.numel()} entries for {c} classes")
+    conf = torch.empty(n, dtype=torch.float32, device=img.device) if want_conf else None
+    thr_arr, n_thr = _lib.doubles(thresholds if thresholds is not None else [])
+    if table is not None:
+        if labels is None or thresholds is None:
+            raise ValueError("labels and thresholds are required when a bin table is requested")
+        labels = _need_cuda("labels", labels, torch.int64, 1)
+        table = _need_cuda("table", table, torch.int64)
+        if table.numel() != 3 * (n_thr + 1) or labels.numel() != n:
+            raise ValueError("table / labels size mismatch")
+    if n:
+        with torch.cuda.device(img.device):
+            rc = lib.ccal_score_pass2(_ptr(img), _ptr(txt), _ptr(class_conf), float(logit_scale), n, c, d,
+                                      _DTYPES[img.dtype], _ptr(dotmax), _ptr(pred), _ptr(conf), None,
+                                      _ptr(labels) if table is not None else None, thr_arr, n_thr, _ptr(table),
+                                      _stream())
+        _lib.check(rc, "ccal_score_pass2")
+    return conf
+
+
 # --------------------------------------------------------------------------------------
 # K5  temperature-scaling loss and gradient
 # --------------------------------------------------------------------------------------

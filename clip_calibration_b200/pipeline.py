@@ -27,6 +27,28 @@ def shard_bounds(n: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device: torch.device) -> torch.cuda.Stream:
+    """One long-lived side stream per device: the caching allocator keeps a block pool per stream, so a fresh stream
+    per call would go back to cudaMalloc (slow, device-synchronising) for every temporary."""
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device: torch.device) -> torch.cuda.Stream:
+    key = (device.type, device.index)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device)
+    return _COPY_STREAMS[key]
+
+
 class CalibratedScorer:
     """Text side of the problem, resident on this rank's GPU, plus the running bin table."""
 
@@ -49,6 +71,8 @@ class CalibratedScorer:
         self._pending_img, self._pending_lab, self._pending_rows = [], [], 0
         # evaluator mode: per-image (pred, conf, label) stay on the device (16 B/image) and per-class {tp, fp, fn}
         # are counted, so that evaluate() can report every key of the reference's evaluator (macro-F1, ACE, PIECE)
+        self._fit_done = None                 # event of a DAC fit still running on a side stream (from_dac(overlap_fit=True))
+        self._text_uploaded = None            # ... and of its host->device uploads
         self.keep_outputs = bool(keep_outputs)
         self._kept = []                       # [(pred int32, conf float32, labels int64)] per scored shard
         self.class_counts = None
@@ -59,13 +83,17 @@ class CalibratedScorer:
         return t.detach().to(self.device).to(self.operand_dtype).contiguous()
 
     @classmethod
-    def from_dac(cls, base_zs, cur_zs, base_tuned, cur_tuned, k: int = 5, share_text: bool = False, **kw):
+    def from_dac(cls, base_zs, cur_zs, base_tuned, cur_tuned, k: int = 5, share_text: bool = False,
+                 overlap_fit: bool = False, **kw):
         """Fit DAC on the four text matrices and score against the tuned test-vocabulary features - what
         VLBaseLearner.test + build_dac_calibrator set up (base_learner.py:117-119, vl_calibrator.py:155-180).
         Host inputs are uploaded once.  By default every rank does this redundantly.  With `share_text` (all ranks
         hold the SAME text features and call together) only rank 0 of the group uploads and fits; the scoring
         operand and the per-class multipliers reach the other ranks by NCCL broadcast over NVLink (51 MB + 0.2 MB
-        at 49,408 x 512) instead of N uploads competing for the host's memory bandwidth."""
+        at 49,408 x 512) instead of N uploads competing for the host's memory bandwidth.
+        With `overlap_fit` (single rank or share_text=False) only the scoring operand is uploaded on the compute
+        stream; the other three matrices and the DAC fit go to a side stream, and `accumulate_host` runs the first
+        chunks' pass 1 (which needs no multipliers) underneath them - the fit leaves the critical path."""
         from .trainers.calibration.distanse_aware_calibration import DistanseAwareCalibration, _to_cuda_f32
         group = kw.get("group")
         shared = (share_text and group is not False and torch.distributed.is_available()
@@ -78,6 +106,28 @@ class CalibratedScorer:
             obj = cls(torch.empty((rows, dim), dtype=dtype, device=dev),
                       torch.empty(rows, dtype=torch.float32, device=dev), **kw)
             obj.dac = None
+        elif overlap_fit and not shared:
+            cur_tuned_dev = _to_cuda_f32(cur_tuned, "current_text_features_tuned")
+            obj = cls(cur_tuned_dev, None, **kw)
+            comp = torch.cuda.current_stream(obj.device)
+            side = _side_stream(obj.device)
+            side.wait_stream(comp)                                   # cur_tuned_dev is produced on the compute stream
+            dac = DistanseAwareCalibration()
+            with torch.cuda.stream(side):
+                rest = [_to_cuda_f32(x, nm) for x, nm in ((base_zs, "base_text_features_zs"),
+                                                          (cur_zs, "current_text_features_zs"),
+                                                          (base_tuned, "base_text_features_tuned"))]
+                # image copies queued later must not overtake these uploads on the copy engine (accumulate_host
+                # orders its copy stream after this event once the first head chunk is on its way)
+                obj._text_uploaded = torch.cuda.Event()
+                obj._text_uploaded.record(side)
+                dac.fit(rest[0], rest[1], rest[2], cur_tuned_dev, k, sync_host_copy=False)
+                obj._fit_done = torch.cuda.Event()
+                obj._fit_done.record(side)
+            cur_tuned_dev.record_stream(side)
+            obj.class_conf = dac.class_confidence_device
+            obj.class_conf.record_stream(comp)
+            obj.dac = dac
         else:
             cur_tuned_dev = _to_cuda_f32(cur_tuned, "current_text_features_tuned")
             dac = DistanseAwareCalibration()
@@ -96,6 +146,12 @@ class CalibratedScorer:
         self._pending_img, self._pending_lab, self._pending_rows = [], [], 0
         self._kept, self.class_counts = [], None
 
+    def _await_fit(self) -> None:
+        """Order the compute stream after a DAC fit that from_dac(overlap_fit=True) left running on a side stream."""
+        if self._fit_done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._fit_done)
+            self._fit_done = None
+
     def _keep(self, pred, conf, labels) -> None:
         if self.class_counts is None:
             self.class_counts = torch.zeros((self.txt.shape[0], 3), dtype=torch.int64, device=self.device)
@@ -110,6 +166,7 @@ class CalibratedScorer:
             labels = (labels if isinstance(labels, torch.Tensor) else torch.from_numpy(np.asarray(labels)))
             labels = labels.to(device=self.device, dtype=torch.int64)
         use_table = labels is not None and accumulate
+        self._await_fit()
         pred, conf, _ = native.score_fused(img, self.txt, self.class_conf, self.logit_scale, labels,
                                            self.thresholds if use_table else None, self.table if use_table else None)
         if use_table and self.keep_outputs:
@@ -134,6 +191,7 @@ class CalibratedScorer:
             img = torch.cat(self._pending_img) if len(self._pending_img) > 1 else self._pending_img[0]
             lab = torch.cat(self._pending_lab) if len(self._pending_lab) > 1 else self._pending_lab[0]
             self._pending_img, self._pending_lab, self._pending_rows = [], [], 0
+            self._await_fit()
             pred, conf, _ = native.score_fused(img, self.txt, self.class_conf, self.logit_scale, lab, self.thresholds,
                                                self.table, want_pred=self.keep_outputs, want_conf=self.keep_outputs)
             if self.keep_outputs:
@@ -155,7 +213,7 @@ class CalibratedScorer:
         labels = labels.to(torch.int64)
         comp = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(self.device)
+            self._copy_stream = _copy_stream(self.device)
         copy = self._copy_stream
         chunk_rows = max(128, min(int(chunk_rows), n))
         bufs = [torch.empty((chunk_rows, d), dtype=self.operand_dtype, device=self.device) for _ in range(2)]
@@ -170,6 +228,40 @@ class CalibratedScorer:
             step = max(128, sizes.pop(0)) if sizes else chunk_rows
             bounds.append((lo, min(n, lo + step)))
             lo += step
+        want_out = keep_outputs or self.keep_outputs
+        if self._fit_done is not None and len(bounds) > 3 and self.operand_dtype in (torch.float16, torch.bfloat16):
+            # The DAC fit is still running on its side stream (from_dac(overlap_fit=True)).  Pass 1 needs no
+            # multipliers: run it on the head chunks as they arrive, underneath the fit and its uploads, then wait
+            # for the fit and finish the head with ONE pass-2 launch.  Same results as the fused launch, bit for bit.
+            head, bounds = bounds[:3], bounds[3:]
+            head_rows = head[-1][1]
+            hbuf = torch.empty((head_rows, d), dtype=self.operand_dtype, device=self.device)
+            hlab = torch.empty(head_rows, dtype=torch.int64, device=self.device)
+            parts = []
+            for j, (lo, hi) in enumerate(head):
+                arrived = torch.cuda.Event()
+                with torch.cuda.stream(copy):
+                    hbuf[lo:hi].copy_(image_features[lo:hi], non_blocking=True)
+                    hlab[lo:hi].copy_(labels[lo:hi], non_blocking=True)
+                    arrived.record(copy)
+                    if j == 0 and self._text_uploaded is not None:
+                        copy.wait_event(self._text_uploaded)         # the fit's inputs go next on the link
+                        self._text_uploaded = None
+                comp.wait_event(arrived)
+                parts.append(native.score_pass1(hbuf[lo:hi], self.txt))
+            dotmax = torch.cat([q[0] for q in parts])
+            pred = torch.cat([q[1] for q in parts])
+            self._await_fit()
+            conf = native.score_pass2(hbuf, self.txt, dotmax, pred, self.class_conf, self.logit_scale, hlab,
+                                      self.thresholds, self.table, want_conf=want_out)
+            hbuf.record_stream(copy)
+            hlab.record_stream(copy)
+            if self.keep_outputs:
+                self._keep(pred, conf, hlab)
+            if keep_outputs:
+                preds.append(pred)
+                confs.append(conf)
+        self._await_fit()
         for i, (lo, hi) in enumerate(bounds):
             b = i & 1
             with torch.cuda.stream(copy):

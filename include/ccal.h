@@ -91,6 +91,19 @@ CCAL_API int ccal_score_fused(const void* img, const void* txt, const float* cla
                      const int64_t* labels, const double* thresholds_host, int n_thr,
                      unsigned long long* table, ccal_stream_t stream);
 
+/* Two-launch form of ccal_score_fused, for pipelines in which the features are on the device before the per-class
+ * multipliers are (the DAC fit still running on another stream): ccal_score_pass1 needs only the features and writes,
+ * per image, the maximum of the RAW dot products (not scaled) and the first argmax; ccal_score_pass2 takes both back
+ * and finishes exactly like ccal_score_fused - confidence, optional scaled row maximum, optional bin table - with
+ * bit-identical results.  fp16 / bf16 operands only; no column-split small-batch mode.
+ */
+CCAL_API int ccal_score_pass1(const void* img, const void* txt, int64_t n, int c, int d, int dtype,
+                     float* rowdot_max_out, int32_t* pred_out, ccal_stream_t stream);
+CCAL_API int ccal_score_pass2(const void* img, const void* txt, const float* class_conf, float logit_scale,
+                     int64_t n, int c, int d, int dtype, const float* rowdot_max_in, const int32_t* pred_in,
+                     float* conf_out, float* rowmax_out, const int64_t* labels, const double* thresholds_host,
+                     int n_thr, unsigned long long* table, ccal_stream_t stream);
+
 /* ---- K5: temperature-scaling objective ------------------------------------------------
  * loss = F.cross_entropy(exp(log_scale) * img @ txt.T, labels) and d loss / d log_scale, for
  * trainers/calibration/tempscaling.py:31-41 (ScaleLearner), :53-56, :155-160.

@@ -668,3 +668,40 @@ def test_vl_calibration_bin_based_multi_isotonic(cuda_lib, golden):
     with pytest.raises(NotImplementedError):
         vl_calibrator.VLCalibration(None, base_calibration_mode="bin_based", base_bin_calibrator_name="histogram_binning",
                                     val_dict=val_dict).fit()
+
+
+def test_two_launch_scoring_is_bit_identical(cuda_lib, golden):
+    """ccal_score_pass1 + ccal_score_pass2 == ccal_score_fused bit for bit (pred, conf, bin table), and
+    from_dac(overlap_fit=True) - the DAC fit on a side stream underneath pass 1 of the head chunks - gives the same
+    table and per-image outputs as the plain path."""
+    case = synth.make_config("sun397_l14", seed=0)
+    img = torch.from_numpy(case.img).cuda().to(torch.bfloat16)
+    txt = torch.from_numpy(case.txt_tuned).cuda().to(torch.bfloat16)
+    labels = torch.from_numpy(case.labels).cuda()
+    cc = torch.from_numpy(np.asarray(golden("sun397_l14")["cc_k5"], dtype=np.float32)).cuda()
+    thr = tm.uniform_thresholds(10)
+    t1, t2 = native.new_table(10), native.new_table(10)
+    pred, conf, _ = native.score_fused(img, txt, cc, case.logit_scale, labels, thr, t1)
+    dotmax, pred2 = native.score_pass1(img, txt)
+    conf2 = native.score_pass2(img, txt, dotmax, pred2, cc, case.logit_scale, labels, thr, t2)
+    assert torch.equal(pred, pred2) and torch.equal(conf, conf2) and torch.equal(t1, t2)
+
+    host_img = img.cpu().pin_memory()
+    host_lab = labels.cpu().pin_memory()
+    outs = []
+    for overlap in (False, True):
+        scorer = pipeline.CalibratedScorer.from_dac(case.base_zs, case.txt_zs, case.base_tuned, case.txt_tuned, k=5,
+                                                    logit_scale=case.logit_scale, operand_dtype=torch.bfloat16,
+                                                    group=False, overlap_fit=overlap)
+        assert (scorer._fit_done is not None) == overlap
+        p, c = scorer.accumulate_host(host_img, host_lab, chunk_rows=1024, keep_outputs=True)
+        assert scorer._fit_done is None
+        outs.append((p.cpu(), c.cpu(), scorer.reduced_table()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+    # a scorer built with overlap_fit and used through score() first simply waits for the fit
+    scorer = pipeline.CalibratedScorer.from_dac(case.base_zs, case.txt_zs, case.base_tuned, case.txt_tuned, k=5,
+                                                logit_scale=case.logit_scale, operand_dtype=torch.bfloat16,
+                                                group=False, overlap_fit=True)
+    p3, c3 = scorer.score(img, labels)
+    assert torch.equal(p3.cpu(), outs[0][0]) and torch.equal(c3.cpu(), outs[0][1])
