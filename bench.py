@@ -383,7 +383,7 @@ def main():
         scorer = pipeline.CalibratedScorer.from_dac(host_txt["bz"], host_txt["cz"], host_txt["bt"], host_txt["ct"],
                                                     k=K_DAC, logit_scale=LOGIT_SCALE, n_bins=N_BINS,
                                                     operand_dtype=torch.bfloat16, share_text=world > 1,
-                                                    overlap_fit=world == 1)
+                                                    overlap_fit=True)
         scorer.accumulate_host(host_img, host_labels, chunk_rows=131072)                     # chunked H2D + scoring
         e2e_table["t"] = scorer.reduced_table()                                              # all-reduce + D2H
 

@@ -91,43 +91,63 @@ class CalibratedScorer:
         hold the SAME text features and call together) only rank 0 of the group uploads and fits; the scoring
         operand and the per-class multipliers reach the other ranks by NCCL broadcast over NVLink (51 MB + 0.2 MB
         at 49,408 x 512) instead of N uploads competing for the host's memory bandwidth.
-        With `overlap_fit` (single rank or share_text=False) only the scoring operand is uploaded on the compute
-        stream; the other three matrices and the DAC fit go to a side stream, and `accumulate_host` runs the first
-        chunks' pass 1 (which needs no multipliers) underneath them - the fit leaves the critical path."""
+        With `overlap_fit` only the scoring operand is uploaded (and, with share_text, broadcast) on the compute
+        stream; the other three matrices, the DAC fit and the broadcast of the multipliers go to a side stream, and
+        `accumulate_host` runs the first chunks' pass 1 (which needs no multipliers) underneath them - the fit
+        leaves the critical path on every rank."""
         from .trainers.calibration.distanse_aware_calibration import DistanseAwareCalibration, _to_cuda_f32
         group = kw.get("group")
         shared = (share_text and group is not False and torch.distributed.is_available()
                   and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1)
-        if shared and torch.distributed.get_rank(group) != 0:
+        is_root = not shared or torch.distributed.get_rank(group) == 0
+        src = (torch.distributed.get_global_rank(group, 0) if group is not None else 0) if shared else None
+
+        def empty_text():
             rows, dim = (int(x) for x in cur_tuned.shape)
             dev = torch.device(kw["device"]) if kw.get("device") is not None else torch.device("cuda", torch.cuda.current_device())
             probe = cur_tuned if isinstance(cur_tuned, torch.Tensor) else torch.from_numpy(np.asarray(cur_tuned)[:1])
-            dtype = native.operand_dtype_for(probe, kw.get("operand_dtype"))
-            obj = cls(torch.empty((rows, dim), dtype=dtype, device=dev),
-                      torch.empty(rows, dtype=torch.float32, device=dev), **kw)
-            obj.dac = None
-        elif overlap_fit and not shared:
-            cur_tuned_dev = _to_cuda_f32(cur_tuned, "current_text_features_tuned")
-            obj = cls(cur_tuned_dev, None, **kw)
+            return torch.empty((rows, dim), dtype=native.operand_dtype_for(probe, kw.get("operand_dtype")), device=dev)
+
+        if overlap_fit:
+            # scoring operand first, on the compute stream (and broadcast at once); everything the multipliers need
+            # goes to the side stream and is awaited by the first launch that uses them
+            cur_tuned_dev = _to_cuda_f32(cur_tuned, "current_text_features_tuned") if is_root else None
+            obj = cls(cur_tuned_dev if is_root else empty_text(), None, **kw)
+            if shared:
+                torch.distributed.broadcast(obj.txt, src=src, group=group)
             comp = torch.cuda.current_stream(obj.device)
             side = _side_stream(obj.device)
             side.wait_stream(comp)                                   # cur_tuned_dev is produced on the compute stream
-            dac = DistanseAwareCalibration()
+            dac = DistanseAwareCalibration() if is_root else None
             with torch.cuda.stream(side):
-                rest = [_to_cuda_f32(x, nm) for x, nm in ((base_zs, "base_text_features_zs"),
-                                                          (cur_zs, "current_text_features_zs"),
-                                                          (base_tuned, "base_text_features_tuned"))]
-                # image copies queued later must not overtake these uploads on the copy engine (accumulate_host
-                # orders its copy stream after this event once the first head chunk is on its way)
-                obj._text_uploaded = torch.cuda.Event()
-                obj._text_uploaded.record(side)
-                dac.fit(rest[0], rest[1], rest[2], cur_tuned_dev, k, sync_host_copy=False)
+                if is_root:
+                    rest = [_to_cuda_f32(x, nm) for x, nm in ((base_zs, "base_text_features_zs"),
+                                                              (cur_zs, "current_text_features_zs"),
+                                                              (base_tuned, "base_text_features_tuned"))]
+                    # image copies queued later must not overtake these uploads on the copy engine
+                    # (accumulate_host orders its copy stream after this event once the first head chunk is on its way)
+                    obj._text_uploaded = torch.cuda.Event()
+                    obj._text_uploaded.record(side)
+                    dac.fit(rest[0], rest[1], rest[2], cur_tuned_dev, k, sync_host_copy=False)
+                    cc = dac.class_confidence_device
+                else:
+                    cc = torch.empty(obj.txt.shape[0], dtype=torch.float32, device=obj.device)
+                if shared:
+                    torch.distributed.broadcast(cc, src=src, group=group)
                 obj._fit_done = torch.cuda.Event()
                 obj._fit_done.record(side)
-            cur_tuned_dev.record_stream(side)
-            obj.class_conf = dac.class_confidence_device
+            if cur_tuned_dev is not None:
+                cur_tuned_dev.record_stream(side)
+            obj.class_conf = cc
             obj.class_conf.record_stream(comp)
             obj.dac = dac
+            return obj
+
+        if not is_root:
+            obj = cls(empty_text(), torch.empty(int(cur_tuned.shape[0]), dtype=torch.float32,
+                                                device=torch.device(kw["device"]) if kw.get("device") is not None
+                                                else torch.device("cuda", torch.cuda.current_device())), **kw)
+            obj.dac = None
         else:
             cur_tuned_dev = _to_cuda_f32(cur_tuned, "current_text_features_tuned")
             dac = DistanseAwareCalibration()
@@ -135,7 +155,6 @@ class CalibratedScorer:
             obj = cls(cur_tuned_dev, dac.class_confidence_device, **kw)
             obj.dac = dac
         if shared:
-            src = torch.distributed.get_global_rank(group, 0) if group is not None else 0
             torch.distributed.broadcast(obj.txt, src=src, group=group)
             torch.distributed.broadcast(obj.class_conf, src=src, group=group)
         return obj

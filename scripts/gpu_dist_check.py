@@ -23,7 +23,7 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["L
 case = synth.make_case("dist", 30011, 1000, 500, 512, 5, 0.25, seed=0)       # same on every rank
 lo, hi = pipeline.shard_bounds(len(case.labels), rank, world)
 scorer = pipeline.CalibratedScorer.from_dac(case.base_zs, case.txt_zs, case.base_tuned, case.txt_tuned, k=5,
-                                            logit_scale=100.0, n_bins=10, share_text=True)   # rank 0 fits, NCCL broadcast
+                                            logit_scale=100.0, n_bins=10, share_text=True, overlap_fit=True)   # rank 0 fits on a side stream, NCCL broadcasts
 pred, conf = scorer.score(case.img[lo:hi], case.labels[lo:hi])
 reduced = scorer.reduced_table()                                               # NCCL all-reduce of 33 int64
 labels_dev = torch.from_numpy(case.labels[lo:hi]).cuda()
