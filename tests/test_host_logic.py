@@ -99,6 +99,22 @@ def test_no_gpu_means_loud_failure():
         native.score_fused(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(4, 64, dtype=torch.bfloat16))
     lib = _lib.load()
     assert lib.ccal_check_device() != 0 and _lib.last_error()
+    # the calibrator wrappers have no CPU path either: every entry that would compute must raise, not fall back
+    with pytest.raises(_lib.CcalError):
+        native.kde2_pdf(*(torch.zeros(3, dtype=torch.float64) for _ in range(4)), 0.1, 0.1)
+    with pytest.raises(_lib.CcalError):
+        native.isotonic_fit_binary(torch.zeros(3, dtype=torch.float64), torch.zeros(3, dtype=torch.uint8))
+    with pytest.raises(_lib.CcalError):
+        native.class_counts(torch.zeros(3, dtype=torch.int32), torch.zeros(3, dtype=torch.int64), 2)
+    with pytest.raises(_lib.CcalError):
+        native.score_pass1(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(4, 64, dtype=torch.bfloat16))
+    from clip_calibration_b200.trainers.calibration.multi_isotonic_regression import MultiIsotonicRegression
+    from clip_calibration_b200.trainers.calibration.density_ratio_calibration import DensityRatioCalibration
+    with pytest.raises((RuntimeError, AssertionError)):
+        MultiIsotonicRegression().fit_transform(np.full((4, 3), 1 / 3), np.array([0, 1, 2, 0]))
+    with pytest.raises((RuntimeError, AssertionError)):
+        DensityRatioCalibration().fit(np.full((4, 3), 1 / 3, np.float32), np.array([0, 1, 2, 0]), np.array([0, 1, 1, 0]),
+                                      np.array([0.3, 0.31, 0.32, 0.33], np.float32))
 
 
 def test_product_code_never_imports_the_oracle():
