@@ -56,7 +56,7 @@ knn_l2_kernel(const float* __restrict__ ref, const float* __restrict__ query, lo
   const int ld_row = tid >> 2, ld_col = (tid & 3) * 4;
   const int cap = min((long long)(k + (drop_first ? 1 : 0)), nr);   // list length actually used
   const long long nq = qlist ? (long long)*qcount : nq_all;
-  const long long q_first = qlist ? kRedoSmallRows : 0;      // list mode: the first rows belong to knn_redo_rows_kernel
+  const long long q_first = qlist ? kRedoSmallRows : 0;      // list mode: the first rows belong to knn_redo_scan_kernel
   for (long long q0 = q_first + (long long)blockIdx.x * kTile; q0 < nq; q0 += (long long)gridDim.x * kTile) {
   // global row of this thread's staged query row (list mode gathers)
   const long long ld_q = (q0 + ld_row < nq) ? (qlist ? (long long)qlist[q0 + ld_row] : q0 + ld_row) : -1;
@@ -326,7 +326,7 @@ int launch_knn_exact(const float* ref, const float* query, int64_t nr, int64_t n
   }
   long long grid = (nq + kTile - 1) / kTile;
   const long long cap = (long long)num_sms() * 4;
-  if (qlist != nullptr && grid > cap) grid = cap;     // list mode: rows beyond the first 256 (normally none)
+  if (qlist != nullptr && grid > cap) grid = cap;     // list mode: rows beyond the first kRedoSmallRows (normally none)
   if (grid > 2147483647ll) grid = 2147483647ll;
   knn_l2_kernel<<<(int)grid, 256, 0, stream>>>(ref, query, (long long)nr, (long long)nq, d, k, drop_first,
                                                dist_out, idx_out, qlist, qcount);
