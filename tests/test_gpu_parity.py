@@ -703,5 +703,8 @@ def test_two_launch_scoring_is_bit_identical(cuda_lib, golden):
     scorer = pipeline.CalibratedScorer.from_dac(case.base_zs, case.txt_zs, case.base_tuned, case.txt_tuned, k=5,
                                                 logit_scale=case.logit_scale, operand_dtype=torch.bfloat16,
                                                 group=False, overlap_fit=True)
+    # reading the multipliers on the host right away must wait for the side-stream fit, not race it
+    cc_now = np.asarray(scorer.dac.class_confidence)
+    np.testing.assert_allclose(cc_now, golden("sun397_l14")["cc_k5"], rtol=3e-6)
     p3, c3 = scorer.score(img, labels)
     assert torch.equal(p3.cpu(), outs[0][0]) and torch.equal(c3.cpu(), outs[0][1])
