@@ -242,3 +242,52 @@ def test_reliability_diagram_data_from_table(golden):
             np.testing.assert_allclose(d["bin_confidences"], cf, rtol=1e-6)
             np.testing.assert_allclose(d["weights"], np.histogram(conf, bins)[0] / len(conf), rtol=1e-12)
             assert abs(d["ece"] - float(g[f"{name}_ece{nb}"])) < 1e-7
+
+
+def _pava_in_rounds(ones, cnt):
+    """numpy statement of what csrc/isotonic.cu does on the device: every maximal run of blocks whose means do not
+    strictly increase is pooled per round (exact integer cross-multiplication), until no run is left."""
+    n = len(ones)
+    start = np.arange(n)
+    rounds = 0
+    while True:
+        viol = np.zeros(len(ones), bool)
+        viol[:-1] = ones[:-1] * cnt[1:] >= ones[1:] * cnt[:-1]
+        if not viol.any():
+            break
+        head = np.ones(len(ones), bool)
+        head[1:] = ~viol[:-1]
+        ids = np.cumsum(head) - 1
+        no, nc = np.zeros(ids[-1] + 1, np.int64), np.zeros(ids[-1] + 1, np.int64)
+        np.add.at(no, ids, ones)
+        np.add.at(nc, ids, cnt)
+        start, ones, cnt = start[head], no, nc
+        rounds += 1
+    fitted = np.empty(n)
+    for s, e, o, c in zip(start, np.append(start[1:], n), ones, cnt):
+        fitted[s:e] = o / c
+    return fitted, rounds
+
+
+@pytest.mark.parametrize("n,ties,seed", [(1, False, 0), (2, False, 1), (500, True, 2), (20000, False, 3), (200000, True, 4)])
+def test_pooling_in_rounds_is_the_isotonic_fit(n, ties, seed):
+    """The round-wise pooling the CUDA isotonic fit uses reaches scikit-learn's sequential PAVA solution
+    (sklearn/_isotonic.pyx) - fitted values, and hence the knots, agree to the last bits - in O(log n)-ish rounds."""
+    from sklearn.isotonic import IsotonicRegression
+    rng = np.random.default_rng(seed)
+    x = rng.random(n)
+    if ties:
+        x = np.round(x * 100) / 100
+    y = (rng.random(n) < x).astype(np.float64)
+    order = np.argsort(x, kind="stable")
+    xs, ys = x[order], y[order]
+    flag = np.ones(n, bool)
+    flag[1:] = (xs[1:] - xs[:-1]) >= 1e-15                       # sklearn _make_unique
+    gid = np.cumsum(flag) - 1
+    ones, cnt = np.zeros(gid[-1] + 1, np.int64), np.zeros(gid[-1] + 1, np.int64)
+    np.add.at(ones, gid, ys.astype(np.int64))
+    np.add.at(cnt, gid, 1)
+    fitted, rounds = _pava_in_rounds(ones, cnt)
+    iso = IsotonicRegression(out_of_bounds="clip").fit(x, y)
+    np.testing.assert_allclose(fitted, iso.predict(xs[flag]), rtol=1e-13, atol=1e-16)
+    assert rounds <= 64
