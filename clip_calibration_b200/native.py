@@ -109,6 +109,15 @@ def score_fused(img: torch.Tensor, txt: torch.Tensor, class_conf: Optional[torch
     return pred, conf, rowmax
 
 
+def score_guess_stats(reset: bool = False):
+    """(rows scored through the FP8-guess -> bf16-verify -> redo pipeline, rows that had to be redone) on the
+    current device since the last reset.  Synchronises the device."""
+    import ctypes
+    out = (ctypes.c_ulonglong * 2)()
+    _lib.check(_lib.load().ccal_score_guess_stats(out, int(bool(reset))), "ccal_score_guess_stats")
+    return int(out[0]), int(out[1])
+
+
 def score_pass1(img: torch.Tensor, txt: torch.Tensor):
     """First half of score_fused: (max of the RAW dot products float32 [N], first argmax int32 [N]).  Needs no
     multipliers, so it can run while the DAC fit is still in flight.  fp16 / bf16 operands."""

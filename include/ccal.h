@@ -91,6 +91,15 @@ CCAL_API int ccal_score_fused(const void* img, const void* txt, const float* cla
                      const int64_t* labels, const double* thresholds_host, int n_thr,
                      unsigned long long* table, ccal_stream_t stream);
 
+/* Large 16-bit shards (n >= 18,944 rows, n*c >= 1e9, d a multiple of 128 and <= 768; CCAL_SCORE_FP8=0/1 in the
+ * environment forces it off / on) run ccal_score_fused as FP8-guess -> bf16-verify -> redo: pass 1 is done on e4m3
+ * copies of the operands and only guesses the argmax; the bf16 pass sums exp at the guessed class's multiplier while
+ * tracking the exact bf16 maximum / first argmax; rows whose exact argmax carries another multiplier are redone
+ * (pass 2 only).  pred_out is exactly the two-pass result; conf_out agrees to a few ulp.
+ * ccal_score_guess_stats: cumulative {rows scored through that pipeline, rows redone} on the current device
+ * (synchronises the device); reset != 0 zeroes the counters afterwards. */
+CCAL_API int ccal_score_guess_stats(unsigned long long* out2_host, int reset);
+
 /* Two-launch form of ccal_score_fused, for pipelines in which the features are on the device before the per-class
  * multipliers are (the DAC fit still running on another stream): ccal_score_pass1 needs only the features and writes,
  * per image, the maximum of the RAW dot products (not scaled) and the first argmax; ccal_score_pass2 takes both back
