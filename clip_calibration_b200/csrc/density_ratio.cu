@@ -123,6 +123,7 @@ density_ratio_rows_kernel(const T* __restrict__ probs, long long n, int c, const
         if (s_v[w] > bv || (s_v[w] == bv && s_i[w] < bi)) { bv = s_v[w]; bi = s_i[w]; }
       __syncthreads();
     }
+    if (bi == 0x7fffffff) bi = 0;                   // row of NaN / -inf only (np.argmax gives 0)
     // sum of the OTHER classes (the reference zeroes the predicted entry before summing)
     double rest = 0.0;
     if (live)

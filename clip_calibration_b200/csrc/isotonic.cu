@@ -5,7 +5,7 @@
 //   exp_normalise_rows   p = exp(v) / sum(exp(v)) per row in float64, no max shift - the reference's own formula
 //                        (multi_isotonic_regression.py:26, :33) - and the flattened one-hot targets.
 //   isotonic_fit_binary  scikit-learn's `_build_y` for 0/1 targets: sort by x (cub radix sort), merge equal x
-//                        (`_make_unique`: a new value starts where x grows by >= 1e-15), pool adjacent violators,
+//                        (`_make_unique`: a new value starts where x - first x of the current value >= 1e-15), pool adjacent violators,
 //                        drop interior points of constant stretches -> knots (X_thresholds_, y_thresholds_).
 //   isotonic_transform   clip to [X_min_, X_max_], linear interpolation between knots (scipy interp1d), plus the
 //                        reference's `+ 1e-9 * p` term.  HBM-bound, 16 B per element.
@@ -77,6 +77,46 @@ __global__ void iso_unique_flags_kernel(const double* __restrict__ xs, long long
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     flag[i] = (i == 0 || xs[i] - xs[i - 1] >= kUniqueEps) ? 1 : 0;
+}
+
+// scikit-learn's `_make_unique` is ANCHORED: a new value starts where x - x_first_of_current_group >= eps, not where
+// two neighbours differ by eps.  Every neighbour-rule flag above is also an anchored start (the anchor is never
+// above the left neighbour), but a run of neighbours closer than eps (dense softmax tails) may hold further starts:
+// next[i] = first j > i with xs[j] - xs[i] >= eps (binary search; the difference is monotone in j), and the starts
+// are the orbit of the flagged positions under `next`.  The orbit is marked by pointer doubling: round r marks
+// next^(2^r) of everything marked so far and squares the jump table, so a run holding g starts needs log2(g) rounds;
+// data without such runs needs one round that marks nothing.
+__global__ void iso_next_kernel(const double* __restrict__ xs, long long n, const int* __restrict__ flag,
+                                int* __restrict__ next) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    long long j = n;
+    if (i + 1 < n) {
+      if (flag[i + 1]) {
+        j = i + 1;
+      } else {
+        const double a = xs[i];
+        long long lo = i + 1, hi = n;                     // first j in (i, n) with xs[j] - a >= eps, else n
+        while (lo < hi) {
+          const long long mid = (lo + hi) >> 1;
+          if (xs[mid] - a >= kUniqueEps) hi = mid; else lo = mid + 1;
+        }
+        j = lo;
+      }
+    }
+    next[i] = (int)j;
+  }
+}
+
+// flag_out is a copy of flag_in on entry; only positions that become marked are written
+__global__ void iso_mark_round_kernel(const int* __restrict__ flag_in, const int* __restrict__ next, long long n,
+                                      int* __restrict__ flag_out, int* __restrict__ next_out, int* __restrict__ changed) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int j = next[i];
+    if (flag_in[i] && j < n && !flag_in[j]) { flag_out[j] = 1; *changed = 1; }
+    next_out[i] = j < n ? next[j] : (int)n;
+  }
 }
 
 // gid = inclusive scan of the flags (1-based group number)
@@ -255,6 +295,26 @@ extern "C" int ccal_isotonic_fit_binary(const double* x, const unsigned char* y,
   note_launch();
   iso_unique_flags_kernel<<<iso_grid(n), kIsoThreads, 0, stream>>>(xs, n, flag);
   note_launch();
+  // anchored starts inside runs of close neighbours (buffers: gid = second flag array, start[] = jump tables)
+  iso_next_kernel<<<iso_grid(n), kIsoThreads, 0, stream>>>(xs, n, flag, start[0]);
+  note_launch();
+  {
+    int* f_cur = flag; int* f_oth = gid;
+    int cur_next = 0;
+    for (int round = 0; round < 40; ++round) {
+      CCAL_CUDA_OK(cudaMemcpyAsync(f_oth, f_cur, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+      CCAL_CUDA_OK(cudaMemsetAsync(small, 0, sizeof(int), stream));
+      iso_mark_round_kernel<<<iso_grid(n), kIsoThreads, 0, stream>>>(f_cur, start[cur_next], n, f_oth, start[cur_next ^ 1], small);
+      note_launch();
+      int changed = 0;
+      CCAL_CUDA_OK(cudaMemcpyAsync(&changed, small, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CCAL_CUDA_OK(cudaStreamSynchronize(stream));
+      if (!changed) break;                         // f_oth == f_cur: the orbit is closed
+      std::swap(f_cur, f_oth);
+      cur_next ^= 1;
+    }
+    if (f_cur != flag) CCAL_CUDA_OK(cudaMemcpyAsync(flag, f_cur, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+  }
   tb = temp_bytes;
   CCAL_CUDA_OK(cub::DeviceScan::InclusiveSum(temp, tb, flag, gid, ni, stream));
   note_launch();

@@ -103,7 +103,7 @@ logits_rows_kernel(float* __restrict__ logits, const float* __restrict__ class_c
       for (int w = 1; w < 8; ++w) m = better(m, s_red[w]);
       __syncthreads();
     }
-    const int pred = m.i;
+    const int pred = (m.i == 0x7fffffff) ? 0 : m.i;   // row of NaN / -inf only: no entry ever compared greater (numpy gives 0)
     const float cc = (live && class_conf) ? class_conf[pred] : 1.0f;
 
     if (OP == kArgmaxOnly) {
@@ -212,7 +212,7 @@ logits_rows_reg_kernel(float* __restrict__ logits, const float* __restrict__ cla
       if (v[u].w > m.v) { m.v = v[u].w; m.i = j + 3; }
     }
     m = group_argmax<32>(m);
-    const int pred = m.i;
+    const int pred = (m.i == 0x7fffffff) ? 0 : m.i;   // row of NaN / -inf only: no entry ever compared greater (numpy gives 0)
     const float cc = class_conf ? __ldg(class_conf + pred) : 1.0f;
     if (OP == kArgmaxOnly) {
       if (lane == 0) {

@@ -521,15 +521,16 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
       if (S > 1) continue;                        // column-split mode, second launch: per-tile partials are out
       // ---------------- per-row results
       if (kMode == 2) {
-        // sum = sum_j 2^(a2 x_j - b2) with b2 = a2 * (guessed maximum); the exact maximum xm rescales it:
-        // conf = 2^(a2 xm - b2) / sum = 1 / sum_j exp(cc s (x_j - xm)).  Final when the exact argmax carries the
-        // multiplier the sum was taken at (it normally IS the guessed class); otherwise the row is listed for the
-        // redo kernel, which repeats pass 2 at the right multiplier from (xm, xarg).
-        const float shift = fmaf(xm, a2, -b2);
+        // The sum was taken at the guessed class's multiplier, shifted by that class's EXACT bf16 dot product m
+        // (guess_logit_kernel).  When the guess is right, m is the row maximum and every term is the very fma / ex2
+        // the two-pass kernel evaluates, so 1 / sum is its confidence bit for bit.  The row is final when the
+        // tracked exact maximum equals m and the first argmax carries the same multiplier (it normally IS the
+        // guessed class; an equal-valued earlier class with an equal multiplier changes nothing); otherwise it is
+        // listed for the redo kernel, which repeats pass 2 from the exact (xm, xarg).
         float cc_exact = 1.0f;
         if (p.class_conf != nullptr && row_ok) cc_exact = __ldg(p.class_conf + xarg);
-        const bool accept = row_ok && cc_exact == cc && fabsf(shift) < 64.f;
-        const float conf = ptx::ex2_approx(shift) / sum;
+        const bool accept = row_ok && xm == m && cc_exact == cc;
+        const float conf = 1.0f / sum;
         if (row_ok) {
           if (p.pred_out) p.pred_out[row] = xarg;
           if (accept) {
@@ -852,6 +853,93 @@ quant_rows_e4m3_kernel(const T* __restrict__ x, long long rows, int d, const int
   }
 }
 
+// Exact bf16 dot product of every image with the text row of its GUESSED class, computed by the tensor core with the
+// accumulation order of the scoring kernels (K ascending in steps of 16 into an fp32 TMEM accumulator), so that it
+// is bit-identical to the logit the verify pass sees in that class's column.  One 128-row tile per CTA: A = the image
+// tile (TMA), B = the 128 guessed text rows gathered into the same swizzled slab layout, D = 128 x 128 of which only
+// the diagonal is read.  0.4 % of one pass's tensor work; two 64-feature slabs per round keep three CTAs per SM.
+constexpr int kDiagThreads = 128;
+constexpr int kDiagSlabs = 2;
+__global__ void __launch_bounds__(kDiagThreads)
+guess_logit_kernel(const __grid_constant__ CUtensorMap map_img, const unsigned char* __restrict__ txt,
+                   const int* __restrict__ guess, long long n, int c, int d, int kblocks, uint32_t idesc,
+                   float* __restrict__ out) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t bar_full, bar_done;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (ptx::smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* op = smem_dyn + (base - ptx::smem_u32(smem_dyn));      // [kDiagSlabs A slabs][kDiagSlabs B slabs]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)blockIdx.x * kBlockM;
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&map_img);
+    ptx::mbar_init(&bar_full, 1);
+    ptx::mbar_init(&bar_done, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) { ptx::tmem_alloc(&tmem_slot, 128); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const long long my_row = row0 + threadIdx.x;
+  int g = (my_row < n) ? guess[my_row] : 0;
+  g = min(max(g, 0), c - 1);
+  const unsigned char* src = txt + (size_t)g * (size_t)d * 2;
+  const int r = threadIdx.x;
+  const int rounds = (kblocks + kDiagSlabs - 1) / kDiagSlabs;
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int kb0 = rd * kDiagSlabs, nkb = min(kDiagSlabs, kblocks - kb0);
+    if (rd > 0) ptx::mbar_wait(&bar_done, (uint32_t)(rd - 1) & 1u);     // the previous round's MMAs have read the slabs
+    if (threadIdx.x == 0) {
+      ptx::mbar_arrive_expect_tx(&bar_full, (uint32_t)nkb * kASlabBytes);
+      for (int s = 0; s < nkb; ++s)
+        ptx::tma_load_2d(op + (size_t)s * kASlabBytes, &map_img, &bar_full, (kb0 + s) * kBlockK, (int)row0, ptx::kEvictNormal);
+    }
+    for (int s = 0; s < nkb; ++s) {
+      const uint4* gsrc = reinterpret_cast<const uint4*>(src + (size_t)(kb0 + s) * 128);
+      unsigned char* slab = op + (size_t)(kDiagSlabs + s) * kASlabBytes;
+      uint4 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = __ldg(gsrc + q);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(slab + r * 128 + ((q ^ (r & 7)) << 4)) = v[q];
+    }
+    ptx::fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      ptx::mbar_wait(&bar_full, (uint32_t)rd & 1u);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        for (int s = 0; s < nkb; ++s) {
+          const uint64_t a_desc = ptx::make_kmajor_sw128_desc(base + (uint32_t)s * kASlabBytes);
+          const uint64_t b_desc = ptx::make_kmajor_sw128_desc(base + (uint32_t)(kDiagSlabs + s) * kASlabBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            ptx::umma_f16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (uint32_t)((rd | s | k) != 0));
+        }
+        ptx::umma_commit(&bar_done);
+      }
+      __syncwarp();
+    }
+  }
+  ptx::mbar_wait(&bar_done, (uint32_t)(rounds - 1) & 1u);
+  ptx::tc_fence_after();
+  {
+    uint32_t raw[32];
+    ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(warp * 32), raw);
+    ptx::tmem_ld_wait(raw);
+    float x = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x = (j == lane) ? __uint_as_float(raw[j]) : x;
+    if (my_row < n) out[my_row] = x;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 128);
+}
+
 __device__ unsigned long long g_guess_stats[2];            // {rows scored through the FP8-guess pipeline, rows redone}
 __global__ void guess_stats_kernel(long long n, const int* __restrict__ redo_count) {
   if (threadIdx.x == 0) { atomicAdd(&g_guess_stats[0], (unsigned long long)n); atomicAdd(&g_guess_stats[1], (unsigned long long)*redo_count); }
@@ -949,6 +1037,18 @@ static int launch_guess_verify(const void* img, const void* txt, int64_t n, int 
     a.part_max = row_max; a.part_arg = guess; a.row_scale_inv = inv_scale;
     a.pred_out = nullptr; a.conf_out = nullptr; a.rowmax_out = nullptr; a.table = nullptr;
     if ((rc = launch_variant<2, true, 0, false, true, false>(map_i8, map_t8, map_i8, map_t8, a, thr, grid_rows, pl.smem, stream))) return rc;
+  }
+  // ---- exact bf16 logit of every row's guessed class (overwrites the FP8 estimate of the row maximum)
+  {
+    CUtensorMap map_img128;
+    if ((rc = make_map(&map_img128, img, n, d, kBlockM, dtype))) return rc;
+    const size_t smem = 1024 + (size_t)2 * kDiagSlabs * kASlabBytes;
+    CCAL_CUDA_OK(cudaFuncSetAttribute(guess_logit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t idesc128 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    guess_logit_kernel<<<(unsigned)((n + kBlockM - 1) / kBlockM), kDiagThreads, smem, stream>>>(
+        map_img128, (const unsigned char*)txt, guess, (long long)n, c, d, d / kBlockK, idesc128, row_max);
+    note_launch();
+    CCAL_CUDA_OK(cudaGetLastError());
   }
   // ---- kernel B: bf16 pass 2 at the guessed multiplier + exact max / argmax; mismatches -> redo list
   p.kblocks = d / kBlockK;

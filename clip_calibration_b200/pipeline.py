@@ -27,6 +27,8 @@ def shard_bounds(n: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+MAX_IMAGES_PER_TABLE = 1 << 24         # 64-bit sum of round(conf * 2^40), conf <= 1
+
 _SIDE_STREAMS = {}
 
 
@@ -102,11 +104,17 @@ class CalibratedScorer:
         is_root = not shared or torch.distributed.get_rank(group) == 0
         src = (torch.distributed.get_global_rank(group, 0) if group is not None else 0) if shared else None
 
+        # The scoring operand's dtype is decided ONCE, from the features as the caller holds them (fp16 / bf16 stay
+        # 16-bit, anything else is scored in the fp32 split mode), and handed to every rank explicitly: the root's
+        # device copy is widened to fp32 for the DAC fit, and inferring the dtype from THAT would make the root
+        # hold an fp32 operand while the other ranks allocate a 16-bit one for the same broadcast.
+        probe = cur_tuned if isinstance(cur_tuned, torch.Tensor) else torch.from_numpy(np.asarray(cur_tuned)[:1])
+        kw = dict(kw, operand_dtype=native.operand_dtype_for(probe, kw.get("operand_dtype")))
+
         def empty_text():
             rows, dim = (int(x) for x in cur_tuned.shape)
             dev = torch.device(kw["device"]) if kw.get("device") is not None else torch.device("cuda", torch.cuda.current_device())
-            probe = cur_tuned if isinstance(cur_tuned, torch.Tensor) else torch.from_numpy(np.asarray(cur_tuned)[:1])
-            return torch.empty((rows, dim), dtype=native.operand_dtype_for(probe, kw.get("operand_dtype")), device=dev)
+            return torch.empty((rows, dim), dtype=kw["operand_dtype"], device=dev)
 
         if overlap_fit:
             # scoring operand first, on the compute stream (and broadcast at once); everything the multipliers need
@@ -314,7 +322,13 @@ class CalibratedScorer:
                 and torch.distributed.get_world_size(self.group) > 1:
             t = t.clone()
             torch.distributed.all_reduce(t, group=self.group)
-        return native.table_to_numpy(t)
+        out = native.table_to_numpy(t)
+        # the per-bin confidence sums are 64-bit fixed point (2^-40 units): 2^24 images of confidence ~1 fill them
+        if tm.total_count(out) > MAX_IMAGES_PER_TABLE:
+            raise OverflowError(f"{tm.total_count(out)} images in one bin table: the 2^-40 fixed-point confidence sums "
+                                f"hold at most {MAX_IMAGES_PER_TABLE}; evaluate in shards of <= 2^24 images "
+                                "(reset() between them) and add the float results")
+        return out
 
     def _reduce_group(self):
         """The process group the tables are reduced over, or None when there is nothing to reduce."""

@@ -38,6 +38,7 @@ class VLCalibration():
         self.text_feature_dict = text_feature_dict
         self.k_dac = cfg.CALIBRATION.DAC.K if cfg is not None else 5
         self.val_dict = val_dict
+        self.val_image_proximity = None          # only the proximity-informed branches need it
         if val_dict is not None and "val_image_knn_dists" in val_dict:
             # distances to proximity (reference :68)
             self.val_image_proximity = np.exp(-np.mean(val_dict["val_image_knn_dists"], axis=-1))
@@ -63,6 +64,7 @@ class VLCalibration():
             val_probs, _, _ = self._val_probs()
             labels = self._val_labels()
             if self.procal_flag:
+                self._need_proximity(val_image_proximity, "bin_based calibration with procal_flag")
                 base_calibrator = BinMeanShift("multi_isotonic_regression", MultiIsotonicRegression,
                                                bin_strategy="quantile", normalize_conf=False, proximity_bin=5)
                 base_calibrator.fit_transform(val_probs, val_image_proximity, labels)
@@ -72,11 +74,18 @@ class VLCalibration():
             return base_calibrator
         if not (self.base_calibration_mode == "scaling_based" and self.procal_flag):
             return None                             # the reference builds nothing in this case either
+        self._need_proximity(val_image_proximity, "scaling_based (density-ratio) calibration")
         val_probs, val_preds, _ = self._val_probs()
         labels = self._val_labels().cpu().numpy()
         base_calibrator = DensityRatioCalibration()
         base_calibrator.fit(val_probs, val_preds.cpu().numpy(), labels, val_image_proximity)
         return base_calibrator
+
+    @staticmethod
+    def _need_proximity(val_image_proximity, what: str) -> None:
+        if val_image_proximity is None:
+            raise ValueError(f"{what} needs val_dict['val_image_knn_dists'] (the validation images' kNN distances, "
+                             "reference vl_calibrator.py:68)")
 
     def _val_probs(self):
         """softmax of the un-scaled validation logits (reference :59-60) as a float32 CUDA matrix, with argmax / max."""

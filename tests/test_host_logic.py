@@ -269,6 +269,55 @@ def _pava_in_rounds(ones, cnt):
     return fitted, rounds
 
 
+def _anchored_unique_flags(xs, eps=1e-15):
+    """numpy statement of csrc/isotonic.cu's grouping: neighbour-rule flags, next[i] = first j > i with
+    xs[j] - xs[i] >= eps, then the orbit of the flagged positions under `next` marked by pointer doubling."""
+    n = len(xs)
+    flag = np.ones(n, bool)
+    flag[1:] = (xs[1:] - xs[:-1]) >= eps
+    nxt = np.empty(n, np.int64)
+    for i in range(n):                                           # the device does this by binary search
+        j = i + 1
+        while j < n and not (xs[j] - xs[i] >= eps):
+            j += 1
+        nxt[i] = j
+    rounds = 0
+    while True:
+        src = np.nonzero(flag)[0]
+        tgt = nxt[src]
+        tgt = tgt[tgt < n]
+        new = tgt[~flag[tgt]]
+        nxt = np.where(nxt < n, np.append(nxt, n)[np.minimum(nxt, n)], n)
+        rounds += 1
+        if len(new) == 0:
+            return flag, rounds
+        flag = flag.copy()
+        flag[new] = True
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_anchored_grouping_matches_sklearn_make_unique(seed):
+    """Dense softmax tails: many values closer than 1e-15 to their neighbours, where scikit-learn starts a new
+    value when x - FIRST x of the current value >= eps (sklearn/_isotonic.pyx::_make_unique) - chaining neighbour
+    differences would merge whole tails into one value."""
+    from sklearn._isotonic import _make_unique
+    rng = np.random.default_rng(seed)
+    x = np.concatenate([rng.random(300) * 4e-14, rng.random(200) * 3e-15, rng.random(100), np.zeros(5),
+                        np.exp(-rng.random(400) * 40.0) * 1e-13])
+    xs = np.sort(x)
+    y = (rng.random(len(xs)) < 0.5).astype(np.float64)
+    flag, rounds = _anchored_unique_flags(xs)
+    ux, uy, uw = _make_unique(xs, y, np.ones_like(xs))
+    assert flag.sum() == len(ux) and np.array_equal(xs[flag], ux)
+    gid = np.cumsum(flag) - 1
+    cnt = np.bincount(gid)
+    assert np.array_equal(cnt.astype(np.float64), uw)
+    neighbour = np.ones(len(xs), bool)
+    neighbour[1:] = (xs[1:] - xs[:-1]) >= 1e-15
+    assert neighbour.sum() < flag.sum(), "the case must exercise the difference between the two rules"
+    assert rounds <= 12
+
+
 @pytest.mark.parametrize("n,ties,seed", [(1, False, 0), (2, False, 1), (500, True, 2), (20000, False, 3), (200000, True, 4)])
 def test_pooling_in_rounds_is_the_isotonic_fit(n, ties, seed):
     """The round-wise pooling the CUDA isotonic fit uses reaches scikit-learn's sequential PAVA solution
