@@ -24,6 +24,7 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int,
                                  c_void_p, c_void_p]),
     "ccal_score_guess_stats": (c_int, [POINTER(ctypes.c_ulonglong), c_int]),
+    "ccal_score_trace": (c_int, [POINTER(ctypes.c_ulonglong), c_int]),
     "ccal_score_pass1": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ccal_score_pass2": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_void_p, c_void_p]),

@@ -170,6 +170,36 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&raw)[32], int nv, flo
 // kSplit (fp32 features, streaming only): every operand arrives as an fp16 pair x*2^e = hi + lo and each K step
 //            issues hi.hi + hi.lo + lo.hi (the dropped lo.lo term is < 2^-22 |a||b|): fp32-grade logits from
 //            16-bit tensor-core operands at 3x the MMA work.
+// In-kernel timing of the scoring launches (bench.py's roofline): every CTA stamps %globaltimer and clock64 when it
+// starts and when it leaves; per kernel kind the library keeps the number of launches, the summed launch spans
+// (first CTA in -> last CTA out), and the CTAs' summed busy nanoseconds and SM cycles, whose ratio is the mean SM
+// clock the kernel actually ran at (nvidia-smi samples every 100 ms and cannot see inside a launch).
+// Launches of one kind are assumed not to overlap each other (they are issued on one stream).
+struct KernelTrace {
+  unsigned long long start_ns, end_ns, done, launches, span_ns, busy_ns, cycles, pad_;
+};
+constexpr int kTraceKinds = 5;          // 0 guess (fp8 pass 1), 1 verify (bf16 pass 2 + exact max), 2 redo, 3 two-pass, 4 temperature scaling
+__device__ KernelTrace g_trace[kTraceKinds] = {{~0ull, 0, 0, 0, 0, 0, 0, 0}, {~0ull, 0, 0, 0, 0, 0, 0, 0}, {~0ull, 0, 0, 0, 0, 0, 0, 0},
+                                               {~0ull, 0, 0, 0, 0, 0, 0, 0}, {~0ull, 0, 0, 0, 0, 0, 0, 0}};
+
+__device__ __forceinline__ void trace_exit(int kind, unsigned long long t0, long long c0) {
+  KernelTrace& tr = g_trace[kind];
+  const unsigned long long t1 = ptx::globaltimer_ns();
+  const long long c1 = clock64();
+  atomicMin(&tr.start_ns, t0);
+  atomicMax(&tr.end_ns, t1);
+  atomicAdd(&tr.busy_ns, t1 - t0);
+  atomicAdd(&tr.cycles, (unsigned long long)(c1 - c0));
+  __threadfence();
+  if (atomicAdd(&tr.done, 1ull) + 1ull == (unsigned long long)gridDim.x) {      // last CTA of this launch
+    __threadfence();
+    const unsigned long long e = atomicExch(&tr.end_ns, 0ull), b = atomicExch(&tr.start_ns, ~0ull);
+    atomicAdd(&tr.span_ns, e - b);
+    atomicAdd(&tr.launches, 1ull);
+    atomicExch(&tr.done, 0ull);
+  }
+}
+
 // Class ranges per row tile of the redo (gather) kernel, derived on the device from the length of the redo list:
 // the smallest S within 2 % of the best wave efficiency, every range at least 4 text tiles long.  The finish
 // kernel evaluates the same function, so both agree without a host round trip.
@@ -247,6 +277,9 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
   if (kCtas == 2) ptx::cluster_sync_all(); else __syncthreads();   // peer barriers initialised before any remote signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
+  unsigned long long trace_t0 = 0;
+  long long trace_c0 = 0;
+  if (threadIdx.x == 0) { trace_t0 = ptx::globaltimer_ns(); trace_c0 = clock64(); }
 
   const int NT = p.n_col_tiles;
   const int KB = p.kblocks;
@@ -574,6 +607,7 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
   if (warp == 1) {
     if (kCtas == 2) ptx::tmem_dealloc_2sm(tmem_base, kTmemCols); else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (threadIdx.x == 0) trace_exit(kFp8 ? 0 : kMode == 2 ? 1 : kGather ? 2 : kMode == 0 ? 3 : 4, trace_t0, trace_c0);
   if (kMode != 1 && p.table != nullptr) {
     for (int i = threadIdx.x; i <= p.n_thr; i += kThreads) {
       const BinCell cell = ctl->cells[i];
@@ -947,11 +981,13 @@ __global__ void guess_stats_kernel(long long n, const int* __restrict__ redo_cou
 
 // shared-memory plan of one variant: operand bytes, ring depth
 struct SmemPlan { int stages; size_t smem; bool resident; };
-static SmemPlan plan_smem(int kblocks, int ctas, bool want_resident, int parts) {
+static SmemPlan plan_smem(int kblocks, int ctas, bool want_resident, int parts, int min_resident_stages = 2) {
   const int avail = kSmemLimit - kCtlBytes - 1024;          // after control block and alignment slack
   const int b_bytes = kBTileBytes / ctas;
   SmemPlan pl;
-  pl.resident = want_resident && (kblocks * kASlabBytes + 2 * b_bytes) <= avail;
+  // a resident image tile next to a ring of fewer than ~4 text stages starves the tensor pipe (measured at d = 768:
+  // 2 stages -> 66 % of the pipe's rate); such shapes stream both operands instead
+  pl.resident = want_resident && (kblocks * kASlabBytes + min_resident_stages * b_bytes) <= avail;
   int stages = pl.resident ? (avail - kblocks * kASlabBytes) / b_bytes : avail / (parts * (kASlabBytes + b_bytes));
   if (stages > kMaxStages) stages = kMaxStages;
   pl.stages = stages;
@@ -1058,7 +1094,7 @@ static int launch_guess_verify(const void* img, const void* txt, int64_t n, int 
   p.part_max = row_max; p.part_arg = guess;
   p.redo_count = redo_count; p.redo_rows = redo_rows;
   {
-    const SmemPlan pl = plan_smem(p.kblocks, ctas, true, 1);
+    const SmemPlan pl = plan_smem(p.kblocks, ctas, true, 1, 4);
     ScoreParams b = p;
     b.stages = pl.stages;
     if (pl.resident) rc = launch_variant<2, true, 2, false>(map_img, map_txt, map_img, map_txt, b, thr, grid_rows, pl.smem, stream);
@@ -1322,6 +1358,24 @@ extern "C" int ccal_score_guess_stats(unsigned long long* out2_host, int reset) 
   if (reset) {
     const unsigned long long zero[2] = {0ull, 0ull};
     CCAL_CUDA_OK(cudaMemcpyToSymbol(g_guess_stats, zero, sizeof(zero)));
+  }
+  return CCAL_OK;
+}
+
+extern "C" int ccal_score_trace(unsigned long long* out_host, int reset) {
+  CCAL_REQUIRE(out_host != nullptr, "ccal_score_trace: NULL output");
+  CCAL_CUDA_OK(cudaDeviceSynchronize());
+  KernelTrace tr[kTraceKinds];
+  CCAL_CUDA_OK(cudaMemcpyFromSymbol(tr, g_trace, sizeof(tr)));
+  for (int k = 0; k < kTraceKinds; ++k) {
+    out_host[4 * k + 0] = tr[k].launches;
+    out_host[4 * k + 1] = tr[k].span_ns;
+    out_host[4 * k + 2] = tr[k].busy_ns;
+    out_host[4 * k + 3] = tr[k].cycles;
+  }
+  if (reset) {
+    for (int k = 0; k < kTraceKinds; ++k) tr[k] = KernelTrace{~0ull, 0, 0, 0, 0, 0, 0, 0};
+    CCAL_CUDA_OK(cudaMemcpyToSymbol(g_trace, tr, sizeof(tr)));
   }
   return CCAL_OK;
 }

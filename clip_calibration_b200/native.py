@@ -118,6 +118,24 @@ def score_guess_stats(reset: bool = False):
     return int(out[0]), int(out[1])
 
 
+TRACE_KINDS = ("guess_fp8", "verify_bf16", "redo", "two_pass", "temperature_scaling")
+
+
+def score_trace(reset: bool = False) -> dict:
+    """In-kernel timing of the scoring kernels since the last reset: {kind: {launches, ms_per_launch (first CTA in ->
+    last CTA out), sm_mhz (the CTAs' cycles / their busy time: the clock the kernel really ran at)}}."""
+    import ctypes
+    out = (ctypes.c_ulonglong * 20)()
+    _lib.check(_lib.load().ccal_score_trace(out, int(bool(reset))), "ccal_score_trace")
+    res = {}
+    for k, name in enumerate(TRACE_KINDS):
+        launches, span, busy, cycles = (int(out[4 * k + j]) for j in range(4))
+        if launches:
+            res[name] = {"launches": launches, "ms_per_launch": span / launches * 1e-6,
+                         "sm_mhz": (cycles / busy * 1e3) if busy else None}
+    return res
+
+
 def score_pass1(img: torch.Tensor, txt: torch.Tensor):
     """First half of score_fused: (max of the RAW dot products float32 [N], first argmax int32 [N]).  Needs no
     multipliers, so it can run while the DAC fit is still in flight.  fp16 / bf16 operands."""

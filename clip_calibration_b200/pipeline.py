@@ -29,6 +29,29 @@ def shard_bounds(n: int, rank: int, world: int):
 
 MAX_IMAGES_PER_TABLE = 1 << 24         # 64-bit sum of round(conf * 2^40), conf <= 1
 
+def dac_fit_sharded(base_zs, cur_zs, base_tuned, cur_tuned, k: int, group=None) -> torch.Tensor:
+    """DAC multipliers [C] (float32, on this rank's GPU) with the fit itself sharded over the ranks of `group`:
+    the classes of the test vocabulary are independent queries against the (replicated) base rows
+    (distanse_aware_calibration.py:25-42 is a loop over them), so rank r fits classes [r*C/W, (r+1)*C/W) and ONE
+    all-gather of C floats hands every rank the full vector.  All four matrices are float32 CUDA tensors and are
+    the same on every rank; the result is identical to the unsharded fit (per-class arithmetic does not depend on
+    which other classes are in the call).  Strong scaling: the fit's share of a step stays constant instead of
+    growing with the rank count."""
+    dist = torch.distributed
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return native.dac_fit(base_zs, cur_zs, base_tuned, cur_tuned, k)[0]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    c = int(cur_zs.shape[0])
+    per = -(-c // world)
+    lo, hi = min(c, rank * per), min(c, (rank + 1) * per)
+    part = torch.ones(per, dtype=torch.float32, device=cur_zs.device)
+    if hi > lo:
+        part[: hi - lo] = native.dac_fit(base_zs, cur_zs[lo:hi].contiguous(), base_tuned, cur_tuned[lo:hi].contiguous(), k)[0]
+    full = torch.empty(per * world, dtype=torch.float32, device=cur_zs.device)
+    dist.all_gather_into_tensor(full, part, group=group)
+    return full[:c].contiguous()
+
+
 _SIDE_STREAMS = {}
 
 

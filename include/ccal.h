@@ -100,6 +100,12 @@ CCAL_API int ccal_score_fused(const void* img, const void* txt, const float* cla
  * (synchronises the device); reset != 0 zeroes the counters afterwards. */
 CCAL_API int ccal_score_guess_stats(unsigned long long* out2_host, int reset);
 
+/* In-kernel timing of the scoring kernels since the last reset, per kind k = 0 FP8 guess pass, 1 bf16 verify pass,
+ * 2 redo, 3 two-pass kernel, 4 temperature-scaling kernel: out_host[4k..4k+3] = {launches, summed launch spans in ns
+ * (first CTA in -> last CTA out, %globaltimer), summed CTA busy ns, summed CTA SM cycles (clock64)} - busy cycles /
+ * busy ns is the SM clock the kernel really ran at.  Synchronises the device.  out_host holds 20 values. */
+CCAL_API int ccal_score_trace(unsigned long long* out_host, int reset);
+
 /* Two-launch form of ccal_score_fused, for pipelines in which the features are on the device before the per-class
  * multipliers are (the DAC fit still running on another stream): ccal_score_pass1 needs only the features and writes,
  * per image, the maximum of the RAW dot products (not scaled) and the first argmax; ccal_score_pass2 takes both back

@@ -255,6 +255,72 @@ def test_fused_scoring_ragged_shapes_fp16_and_bf16(cuda_lib, n, c, d, score_ctas
         check_scoring(case, cc, pref, cref, gap, ece_ref, counts, dtype)
 
 
+def _device_case(n, c, d, signal, dtype, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    unit = lambda x: x / x.norm(dim=-1, keepdim=True)
+    u = unit(torch.randn(d, device="cuda", generator=g))
+    txt = unit(u[None, :] + 0.6 / d ** 0.5 * torch.randn(c, d, device="cuda", generator=g)).to(dtype)
+    labels = torch.randint(0, c, (n,), device="cuda", generator=g)
+    img = torch.empty((n, d), dtype=dtype, device="cuda")
+    for lo in range(0, n, 65536):
+        hi = min(n, lo + 65536)
+        raw = signal * txt[labels[lo:hi]].float() + torch.randn(hi - lo, d, device="cuda", generator=g) / d ** 0.5
+        img[lo:hi] = unit(raw).to(dtype)
+    cc = (0.97 + 0.03 * torch.rand(c, device="cuda", generator=g)).float()
+    cc[: c // 3] = 1.0
+    return img, txt.contiguous(), labels, cc
+
+
+@pytest.mark.parametrize("n,c,d,signal,dtype,use_cc", [
+    (3000, 2048, 512, 0.4, torch.bfloat16, True),        # few rows: the redo kernel cuts its tiles into class ranges
+    (50_000, 8192, 512, 0.4, torch.bfloat16, True),
+    (60_000, 21841, 768, 0.45, torch.bfloat16, True),    # d = 768: streaming verify pass, 2-stage redo kernel
+    (33_333, 5000, 640, 0.3, torch.bfloat16, True),      # ragged everything
+    (30_000, 4096, 256, 0.3, torch.float16, True),
+    (20_000, 3000, 128, 0.3, torch.bfloat16, False),     # no multipliers: redo only where the guess missed the maximum
+    (320_000, 2048, 128, 0.02, torch.bfloat16, True),    # near-random labels: > 32,768 rows redone (no class ranges)
+])
+def test_fp8_guess_pipeline_is_bit_identical_to_two_pass(cuda_lib, n, c, d, signal, dtype, use_cc, monkeypatch):
+    """ccal_score_fused through the FP8-guess -> exact-logit -> bf16-verify -> redo pipeline (what large shards run)
+    against the plain two-pass kernel on the same inputs: labels, confidences, row maxima and the bin table are
+    identical bit for bit, whatever the guess quality; a row's result does not depend on how the shard is cut."""
+    img, txt, labels, cc = _device_case(n, c, d, signal, dtype, seed=n + c)
+    if not use_cc:
+        cc = None
+    thr = tm.uniform_thresholds(15)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CCAL_SCORE_FP8", mode)
+        native.score_guess_stats(reset=True)
+        table = native.new_table(15)
+        pred, conf, rowmax = native.score_fused(img, txt, cc, 100.0, labels, thr, table, want_rowmax=True)
+        outs[mode] = (pred, conf, rowmax, table, native.score_guess_stats(reset=True))
+    p0, c0, r0, t0, s0 = outs["0"]
+    p1, c1, r1, t1, s1 = outs["1"]
+    assert s0 == (0, 0) and s1[0] == n
+    assert 0 < s1[1] < 0.6 * n, f"redo count {s1[1]} of {n}: the FP8 guess or the exact guessed-class logit is off"
+    assert torch.equal(p0, p1) and torch.equal(c0, c1) and torch.equal(r0, r1) and torch.equal(t0, t1)
+    assert tm.total_count(native.table_to_numpy(t1)) == n
+    # outputs are optional, sub-shards give the same rows, and the table accumulates
+    m = n // 3
+    t2 = native.new_table(15)
+    p2, c2, _ = native.score_fused(img[:m].contiguous(), txt, cc, 100.0, labels[:m].contiguous(), thr, t2)
+    native.score_fused(img[m:].contiguous(), txt, cc, 100.0, labels[m:].contiguous(), thr, t2, want_pred=False, want_conf=False)
+    assert torch.equal(p2, p1[:m]) and torch.equal(c2, c1[:m]) and torch.equal(t2, t1)
+    monkeypatch.delenv("CCAL_SCORE_FP8")
+
+
+def test_fp8_guess_pipeline_on_the_open_vocabulary_golden(cuda_lib, golden, synth_case, monkeypatch):
+    """The reference-generated open-vocabulary fixture (1,024 rows x 49,408 classes) through the forced pipeline."""
+    monkeypatch.setenv("CCAL_SCORE_FP8", "1")
+    g, case = golden("openvocab"), synth_case("openvocab")
+    native.score_guess_stats(reset=True)
+    check_scoring(case, g["cc_k5"], g["dac_pred"], g["dac_conf"], g["dac_gap"], float(g["dac_ece10"]), g["dac_counts10"])
+    check_scoring(case, None, g["nodac_pred"], g["nodac_conf"], g["nodac_gap"], float(g["nodac_ece10"]), g["nodac_counts10"])
+    assert native.score_guess_stats(reset=True)[0] > 0
+    monkeypatch.delenv("CCAL_SCORE_FP8")
+
+
 @pytest.mark.parametrize("n,c,d,dtype", [(100, 49408, 512, torch.bfloat16), (1, 3000, 64, torch.float16), (1000, 21841, 768, torch.bfloat16),
                                          (4097, 5000, 512, torch.bfloat16), (300, 2049, 128, torch.float32)])
 def test_column_split_mode_for_small_batches(cuda_lib, n, c, d, dtype, monkeypatch):
@@ -608,6 +674,29 @@ def test_multi_isotonic_regression_matches_reference_fixture(cuda_lib, golden):
     onehot = (d["val_labels"][:, None] == np.arange(vp.shape[1])[None]).astype(np.float64)
     cal2 = MultiIsotonicRegression()
     np.testing.assert_allclose(cal2.fit_transform(vp, onehot), val_out, rtol=0, atol=0)
+
+
+def test_isotonic_fit_on_dense_softmax_tails(cuda_lib):
+    """Exp-normalised logits: thousands of tail values closer than 1e-15 to their neighbours.  scikit-learn starts a
+    new x value where x - FIRST x of the current value >= 1e-15 (anchored), not where neighbours differ by that
+    much; the knots and the transform must follow it (79 knots against sklearn's 96 with the chained rule)."""
+    from sklearn.isotonic import IsotonicRegression
+    rng = np.random.default_rng(5)
+    n, c = 4000, 100
+    logits = rng.standard_normal((n, c)) * 9.0
+    labels = torch.from_numpy(rng.integers(0, c, n))
+    probs, onehot = native.exp_normalise_rows(torch.from_numpy(logits).cuda(), labels.cuda())
+    x = probs.cpu().numpy().ravel()
+    y = onehot.cpu().numpy().ravel()
+    xs = np.sort(x)
+    assert ((xs[1:] - xs[:-1]) < 1e-15).sum() > 10000, "the case must contain dense tails"
+    iso = IsotonicRegression(out_of_bounds="clip").fit(x, y.astype(np.float64))
+    kx, ky = native.isotonic_fit_binary(probs.reshape(-1), onehot.reshape(-1))
+    np.testing.assert_allclose(kx.cpu().numpy(), iso.X_thresholds_, rtol=0, atol=0)
+    np.testing.assert_allclose(ky.cpu().numpy(), iso.y_thresholds_, rtol=1e-13, atol=1e-16)
+    t = rng.random(5000)
+    got = native.isotonic_transform(kx, ky, torch.from_numpy(t).cuda()).cpu().numpy()
+    np.testing.assert_allclose(got, iso.predict(t), rtol=1e-12, atol=1e-15)
 
 
 @pytest.mark.parametrize("n,c,seed", [(1, 2, 0), (50, 3, 1), (400, 10, 2), (3000, 100, 3), (20000, 120, 4)])
