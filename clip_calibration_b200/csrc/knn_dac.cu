@@ -294,6 +294,13 @@ __device__ __forceinline__ float numpy_sum_f32(const float* a, int n) {
   return res;
 }
 
+__device__ __forceinline__ float dac_map_value(const float* a, const float* b, int k, int kk) {
+  const float kf = (float)k;                              // divides by k even when kk < k
+  const float zs_score = expf(-__fdiv_rn(numpy_sum_f32(a, kk), kf));
+  const float fs_score = expf(-__fdiv_rn(numpy_sum_f32(b, kk), kf));
+  return ((double)b[0] < 0.05) ? 1.0f : __fdiv_rn(fs_score, zs_score);
+}
+
 // class_conf[i] = 1 if nearest tuned distance < 0.05 else exp(-sum(tuned)/k) / exp(-sum(zs)/k)
 __global__ void dac_map_kernel(const float* __restrict__ dist_zs, const float* __restrict__ dist_tuned,
                                int c, int k, int kk, float* __restrict__ class_conf) {
@@ -301,10 +308,190 @@ __global__ void dac_map_kernel(const float* __restrict__ dist_zs, const float* _
   if (i >= c) return;
   float a[CCAL_MAX_K], b[CCAL_MAX_K];
   for (int j = 0; j < kk; ++j) { a[j] = dist_zs[(long long)i * k + j]; b[j] = dist_tuned[(long long)i * k + j]; }
-  const float kf = (float)k;                              // divides by k even when kk < k
-  const float zs_score = expf(-__fdiv_rn(numpy_sum_f32(a, kk), kf));
-  const float fs_score = expf(-__fdiv_rn(numpy_sum_f32(b, kk), kf));
-  class_conf[i] = ((double)b[0] < 0.05) ? 1.0f : __fdiv_rn(fs_score, zs_score);
+  class_conf[i] = dac_map_value(a, b, k, kk);
+}
+
+// ---- small DAC fits in ONE launch -------------------------------------------------------------------------
+// EuroSAT / SUN397 / ImageNet-sized vocabularies (C x B up to ~2M pairs) are latency-bound: the general path is a
+// chain of ~19 launches (two kNN problems x {split, tensor-core filter, verify, redo, ...} + the map) of which each
+// does microseconds of work.  Here one launch does everything: CTA = (problem, 64-query tile, 64-reference tile)
+// computes its exact fp32 distance tile (the tiled scan's arithmetic: features in ascending order, fma of squared
+// differences, so the floats are those of ccal_knn_l2_exhaustive) and leaves a sorted partial list per query row;
+// the LAST CTA of a query tile (atomic ticket) merges the partial lists by (distance, index) and writes the
+// neighbours; the last of the two problems then applies the DAC map to the tile's 64 classes.
+struct DacSmallParams {
+  const float* ref[2];
+  const float* qry[2];
+  float* dist[2];
+  int* idx[2];
+  int b, c, d, k, cap, n_qt, n_rt;
+  float* part_d;               // [2][c][n_rt][cap]
+  int* part_i;
+  unsigned int* tickets;       // [2 * n_qt] per (problem, query tile) + [n_qt] per query tile, zeroed by the host
+  float* class_conf;
+};
+
+__global__ void __launch_bounds__(256)
+dac_fit_small_kernel(const __grid_constant__ DacSmallParams P) {
+  __shared__ __align__(16) float Qs[kChunk][kPad];
+  __shared__ __align__(16) float Rs[kChunk][kPad];
+  __shared__ float Dt[kTile][kTile + 1];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int ld_row = tid >> 2, ld_col = (tid & 3) * 4;
+  const int per = P.n_qt * P.n_rt;
+  const int prob = blockIdx.x / per, qt = (blockIdx.x % per) / P.n_rt, rt = blockIdx.x % P.n_rt;
+  const float* __restrict__ ref = P.ref[prob];
+  const float* __restrict__ query = P.qry[prob];
+  const int d = P.d, cap = P.cap;
+  const long long q0 = (long long)qt * kTile, r0 = (long long)rt * kTile;
+  const long long ld_q = (q0 + ld_row < P.c) ? q0 + ld_row : -1;
+
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) acc[a][bb] = 0.f;
+  float4 qv[kChunk / 16], rv[kChunk / 16];
+  auto load_chunk = [&](int d0) {
+#pragma unroll
+    for (int h = 0; h < kChunk / 16; ++h) {
+      qv[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rv[h] = qv[h];
+      const int dc = d0 + 16 * h + ld_col;
+      if (dc < d) {
+        if (ld_q >= 0) qv[h] = *reinterpret_cast<const float4*>(query + ld_q * d + dc);
+        if (r0 + ld_row < P.b) rv[h] = *reinterpret_cast<const float4*>(ref + (r0 + ld_row) * d + dc);
+      }
+    }
+  };
+  load_chunk(0);
+  for (int d0 = 0; d0 < d; d0 += kChunk) {
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < kChunk / 16; ++h) {
+      const int c0 = 16 * h + ld_col;
+      Qs[c0 + 0][ld_row] = qv[h].x; Qs[c0 + 1][ld_row] = qv[h].y;
+      Qs[c0 + 2][ld_row] = qv[h].z; Qs[c0 + 3][ld_row] = qv[h].w;
+      Rs[c0 + 0][ld_row] = rv[h].x; Rs[c0 + 1][ld_row] = rv[h].y;
+      Rs[c0 + 2][ld_row] = rv[h].z; Rs[c0 + 3][ld_row] = rv[h].w;
+    }
+    __syncthreads();
+    if (d0 + kChunk < d) load_chunk(d0 + kChunk);
+#pragma unroll
+    for (int kk = 0; kk < kChunk; ++kk) {
+      const float4 q4 = *reinterpret_cast<const float4*>(&Qs[kk][ty * 4]);
+      const float4 r4 = *reinterpret_cast<const float4*>(&Rs[kk][tx * 4]);
+      const float qa[4] = {q4.x, q4.y, q4.z, q4.w};
+      const float ra[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const float df = ra[bb] - qa[a];
+          acc[a][bb] = fmaf(df, df, acc[a][bb]);
+        }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) Dt[ty * 4 + a][tx * 4 + bb] = sqrtf(acc[a][bb]);
+  __syncthreads();
+
+  // sorted partial list (by distance, then index) of every query row over this reference tile
+#pragma unroll 1
+  for (int r = 0; r < kRowsPerWarp; ++r) {
+    const int row = warp * kRowsPerWarp + r;
+    const long long q = q0 + row;
+    TopList mine{CUDART_INF_F, 0x7fffffff};
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int col = lane + 32 * half;
+      const bool ok = r0 + col < P.b;
+      list_offer(mine, ok ? Dt[row][col] : CUDART_INF_F, ok ? (int)(r0 + col) : -1, cap, lane);
+    }
+    if (q < P.c && lane < cap) {
+      const long long o = (((long long)prob * P.c + q) * P.n_rt + rt) * cap + lane;
+      P.part_d[o] = mine.d;
+      P.part_i[o] = mine.i;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&P.tickets[prob * P.n_qt + qt], 1u) == (unsigned)(P.n_rt - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  // merge the partial lists of this query tile
+  const int k = P.k;
+#pragma unroll 1
+  for (int r = 0; r < kRowsPerWarp; ++r) {
+    const long long q = q0 + warp * kRowsPerWarp + r;
+    if (q >= P.c) continue;                              // warp-uniform
+    TopList all{CUDART_INF_F, 0x7fffffff};
+    const int total = P.n_rt * cap;
+    const long long o = ((long long)prob * P.c + q) * total;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      const float cd = t < total ? __ldcg(P.part_d + o + t) : CUDART_INF_F;
+      const int ci = t < total ? __ldcg(P.part_i + o + t) : -1;
+      list_offer(all, cd, ci == 0x7fffffff ? -1 : ci, cap, lane);
+    }
+    if (lane < k) {
+      const bool have = lane < cap;
+      P.dist[prob][q * k + lane] = have ? all.d : CUDART_INF_F;
+      if (P.idx[prob]) P.idx[prob][q * k + lane] = have ? all.i : -1;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&P.tickets[2 * P.n_qt + qt], 1u) == 1u);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < kTile && q0 + tid < P.c) {
+    const long long i = q0 + tid;
+    float a[CCAL_MAX_K], bvals[CCAL_MAX_K];
+    for (int j = 0; j < cap; ++j) { a[j] = __ldcg(P.dist[0] + i * k + j); bvals[j] = __ldcg(P.dist[1] + i * k + j); }
+    P.class_conf[i] = dac_map_value(a, bvals, k, cap);
+  }
+}
+
+static bool small_fit_applies(int b, int c, int d) {
+  if (getenv("CCAL_DAC_NO_SMALL_FIT")) return false;
+  return (long long)b * (long long)c <= (1ll << 21) && b <= kTile * 64 && d % 4 == 0;
+}
+
+static int launch_dac_fit_small(const float* base_zs, const float* cur_zs, const float* base_tuned, const float* cur_tuned,
+                                int b, int c, int d, int k, float* class_conf, int32_t* idx_zs, int32_t* idx_tuned,
+                                float* dist_zs, float* dist_tuned, cudaStream_t stream) {
+  DacSmallParams P{};
+  P.ref[0] = base_zs; P.ref[1] = base_tuned;
+  P.qry[0] = cur_zs; P.qry[1] = cur_tuned;
+  P.dist[0] = dist_zs; P.dist[1] = dist_tuned;
+  P.idx[0] = idx_zs; P.idx[1] = idx_tuned;
+  P.b = b; P.c = c; P.d = d; P.k = k;
+  P.cap = k < b ? k : b;
+  P.n_qt = (c + kTile - 1) / kTile;
+  P.n_rt = (b + kTile - 1) / kTile;
+  P.class_conf = class_conf;
+  const size_t cells = (size_t)2 * c * P.n_rt * P.cap;
+  const size_t o_i = (cells * sizeof(float) + 255) & ~(size_t)255;
+  const size_t o_t = (o_i + cells * sizeof(int) + 255) & ~(size_t)255;
+  const size_t ticket_bytes = (size_t)3 * P.n_qt * sizeof(unsigned int);
+  AsyncWorkspace ws;
+  CCAL_CUDA_OK(ws.alloc(o_t + ticket_bytes, stream));
+  P.part_d = reinterpret_cast<float*>(ws.ptr);
+  P.part_i = reinterpret_cast<int*>(ws.ptr + o_i);
+  P.tickets = reinterpret_cast<unsigned int*>(ws.ptr + o_t);
+  CCAL_CUDA_OK(cudaMemsetAsync(P.tickets, 0, ticket_bytes, stream));
+  dac_fit_small_kernel<<<2 * P.n_qt * P.n_rt, 256, 0, stream>>>(P);
+  note_launch();
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
 }
 
 int launch_knn_exact(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k, int drop_first,
@@ -386,6 +573,9 @@ extern "C" int ccal_dac_fit(const float* base_zs, const float* cur_zs, const flo
   CCAL_REQUIRE(base_zs && cur_zs && base_tuned && cur_tuned && class_conf_out, "ccal_dac_fit: NULL input");
   CCAL_REQUIRE(knn_dist_zs_out && knn_dist_tuned_out,
                "ccal_dac_fit: the two [c,k] distance buffers are required (they double as workspace)");
+  if (small_fit_applies(b, c, d))
+    return launch_dac_fit_small(base_zs, cur_zs, base_tuned, cur_tuned, b, c, d, k, class_conf_out, knn_idx_zs_out,
+                                knn_idx_tuned_out, knn_dist_zs_out, knn_dist_tuned_out, stream);
   int rc = launch_knn(base_zs, cur_zs, b, c, d, k, 0, knn_dist_zs_out, knn_idx_zs_out, stream);
   if (rc) return rc;
   rc = launch_knn(base_tuned, cur_tuned, b, c, d, k, 0, knn_dist_tuned_out, knn_idx_tuned_out, stream);
