@@ -30,12 +30,17 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int, c_void_p, c_void_p]),
     "ccal_ts_loss_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int, c_int, c_int,
                                   c_void_p, c_void_p, c_void_p]),
+    "ccal_ts_loss_grad_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_void_p]),
+    "ccal_sgd_scalar_step": (c_int, [c_void_p, c_void_p, c_double, c_double, c_double, c_void_p]),
     "ccal_knn_l2": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
                             c_void_p]),
     "ccal_knn_l2_exhaustive": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_void_p]),
     "ccal_dac_fit": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ccal_dac_fit_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ccal_dac_predict_logits": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "ccal_logits_confidence": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "ccal_dac_softmax_logits": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

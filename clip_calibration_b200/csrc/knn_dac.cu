@@ -10,6 +10,7 @@
 // Ties: lower reference index first.
 #include "ccal_common.cuh"
 
+#include <cuda_fp16.h>
 #include <math_constants.h>
 #include <algorithm>
 
@@ -460,6 +461,124 @@ dac_fit_small_kernel(const __grid_constant__ DacSmallParams P) {
   }
 }
 
+// ---- DAC fit in the reference's float16 arithmetic ----------------------------------------------------------
+// The reference's default precision is fp16 (train.py:152), its cached text features are float16 numpy arrays, and
+// np.linalg.norm / np.sum / np.exp keep that dtype: every elementwise result is rounded to
+// half, the squares are summed in float32 in numpy's pairwise order and rounded to half once per row.  The float32
+// path above is closer to the exact answer, but differs from what the reference computes by up to 1e-3 relative in
+// class_confidence; this kernel reproduces numpy's half arithmetic operation by operation (opt-in:
+// DistanseAwareCalibration.fit(..., arithmetic="input")).  One CTA per class, one thread per base row.
+__device__ __forceinline__ float half_sq_term(__half r, float q) {
+  const float diff = __half2float(__float2half_rn(__fsub_rn(__half2float(r), q)));     // HALF_subtract
+  return __half2float(__float2half_rn(__fmul_rn(diff, diff)));                         // HALF_multiply
+}
+
+// numpy's pairwise_sum over the n rounded squares of one row (float32 accumulation; numpy/core/src/umath/loops_utils.h)
+__device__ float half_row_pairwise(const __half* __restrict__ r, const float* __restrict__ q, int n) {
+  if (n < 8) {
+    float res = 0.f;
+    for (int i = 0; i < n; ++i) res = __fadd_rn(res, half_sq_term(r[i], q[i]));
+    return res;
+  }
+  if (n <= 128) {
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = half_sq_term(r[j], q[j]);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = __fadd_rn(a[j], half_sq_term(r[i + j], q[i + j]));
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])),
+                          __fadd_rn(__fadd_rn(a[4], a[5]), __fadd_rn(a[6], a[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, half_sq_term(r[i], q[i]));
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return __fadd_rn(half_row_pairwise(r, q, n2), half_row_pairwise(r + n2, q + n2, n - n2));
+}
+
+constexpr int kHalfFitMaxBase = 16384;
+
+__global__ void __launch_bounds__(256)
+dac_fit_half_kernel(const __half* __restrict__ base_zs, const __half* __restrict__ cur_zs,
+                    const __half* __restrict__ base_tuned, const __half* __restrict__ cur_tuned, int b, int c, int d, int k,
+                    float* __restrict__ class_conf, int* __restrict__ idx_zs, int* __restrict__ idx_tuned,
+                    float* __restrict__ dist_zs, float* __restrict__ dist_tuned) {
+  extern __shared__ __align__(16) unsigned char half_fit_smem[];
+  float* s_q = reinterpret_cast<float*>(half_fit_smem);                     // [d] the class's feature row
+  unsigned short* s_d = reinterpret_cast<unsigned short*>(s_q + d);         // [b] distances (half bits; non-negative)
+  __shared__ unsigned int s_best[8];
+  __shared__ int s_besti[8];
+  __shared__ float s_top[2][CCAL_MAX_K];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kk = k < b ? k : b;
+  for (int cls = blockIdx.x; cls < c; cls += gridDim.x) {
+    for (int prob = 0; prob < 2; ++prob) {
+      const __half* base = prob ? base_tuned : base_zs;
+      const __half* cur = (prob ? cur_tuned : cur_zs) + (size_t)cls * d;
+      __syncthreads();
+      for (int j = tid; j < d; j += 256) s_q[j] = __half2float(cur[j]);
+      __syncthreads();
+      for (int r = tid; r < b; r += 256) {
+        const float s = half_row_pairwise(base + (size_t)r * d, s_q, d);
+        const __half s16 = __float2half_rn(s);                               // HALF_add reduce: one rounding per row
+        const __half dist = __float2half_rn(sqrtf(__half2float(s16)));       // np.sqrt on float16
+        s_d[r] = __half_as_ushort(dist);
+      }
+      __syncthreads();
+      // k rounds of (distance, index) arg-min; non-negative halves order like their bit patterns
+      for (int t = 0; t < kk; ++t) {
+        unsigned int best = 0xffffffffu;
+        int besti = 0x7fffffff;
+        for (int r = tid; r < b; r += 256) {
+          const unsigned int v = s_d[r];
+          if (v < best) { best = v; besti = r; }                             // ascending r per thread: first index wins
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const unsigned int ov = __shfl_xor_sync(0xffffffffu, best, off);
+          const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+          if (ov < best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        if (lane == 0) { s_best[warp] = best; s_besti[warp] = besti; }
+        __syncthreads();
+        if (tid == 0) {
+          for (int w = 1; w < 8; ++w)
+            if (s_best[w] < best || (s_best[w] == best && s_besti[w] < besti)) { best = s_best[w]; besti = s_besti[w]; }
+          const float dv = __half2float(__ushort_as_half((unsigned short)best));
+          s_top[prob][t] = dv;
+          float* dout = prob ? dist_tuned : dist_zs;
+          int* iout = prob ? idx_tuned : idx_zs;
+          if (dout) dout[(size_t)cls * k + t] = dv;
+          if (iout) iout[(size_t)cls * k + t] = besti;
+          s_d[besti] = 0xffffu;                                              // taken (above every finite half / inf)
+        }
+        __syncthreads();
+      }
+      if (tid == 0)
+        for (int t = kk; t < k; ++t) {
+          float* dout = prob ? dist_tuned : dist_zs;
+          int* iout = prob ? idx_tuned : idx_zs;
+          if (dout) dout[(size_t)cls * k + t] = CUDART_INF_F;
+          if (iout) iout[(size_t)cls * k + t] = -1;
+        }
+    }
+    if (tid == 0) {
+      float score[2];
+      for (int prob = 0; prob < 2; ++prob) {
+        const __half sum16 = __float2half_rn(numpy_sum_f32(s_top[prob], kk));            // np.sum on float16
+        const __half q16 = __float2half_rn(__fdiv_rn(-__half2float(sum16), (float)k));   // -sum / k (k <= 16 is exact in half)
+        score[prob] = __half2float(__float2half_rn((float)exp((double)__half2float(q16))));   // np.exp on float16
+      }
+      const float thr = __half2float(__float2half_rn(0.05f));      // NEP 50: the Python float is compared as float16
+      const __half ratio = __float2half_rn(__fdiv_rn(score[1], score[0]));
+      class_conf[cls] = (s_top[1][0] < thr) ? 1.0f : __half2float(ratio);
+    }
+  }
+}
+
 static bool small_fit_applies(int b, int c, int d) {
   if (getenv("CCAL_DAC_NO_SMALL_FIT")) return false;
   return (long long)b * (long long)c <= (1ll << 21) && b <= kTile * 64 && d % 4 == 0;
@@ -582,6 +701,30 @@ extern "C" int ccal_dac_fit(const float* base_zs, const float* cur_zs, const flo
   if (rc) return rc;
   const int kk = k < b ? k : b;
   dac_map_kernel<<<(c + 127) / 128, 128, 0, stream>>>(knn_dist_zs_out, knn_dist_tuned_out, c, k, kk, class_conf_out);
+  note_launch();
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}
+
+extern "C" int ccal_dac_fit_f16(const void* base_zs, const void* cur_zs, const void* base_tuned, const void* cur_tuned,
+                                int b, int c, int d, int k, float* class_conf_out, int32_t* knn_idx_zs_out,
+                                int32_t* knn_idx_tuned_out, float* knn_dist_zs_out, float* knn_dist_tuned_out,
+                                ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE(b >= 1 && c >= 0, "ccal_dac_fit_f16: bad class counts b=%d c=%d", b, c);
+  CCAL_REQUIRE(b <= kHalfFitMaxBase, "ccal_dac_fit_f16: at most %d base classes (got %d)", kHalfFitMaxBase, b);
+  CCAL_REQUIRE(d >= 1 && d <= 4096, "ccal_dac_fit_f16: d must be in 1..4096 (got %d)", d);
+  CCAL_REQUIRE(k >= 1 && k <= CCAL_MAX_K, "ccal_dac_fit_f16: k must be in 1..%d (got %d)", CCAL_MAX_K, k);
+  if (c == 0) return CCAL_OK;
+  CCAL_REQUIRE(base_zs && cur_zs && base_tuned && cur_tuned && class_conf_out, "ccal_dac_fit_f16: NULL input");
+  int rc = ccal_check_device();
+  if (rc) return rc;
+  const size_t smem = (size_t)d * sizeof(float) + (size_t)b * sizeof(unsigned short) + 16;
+  CCAL_CUDA_OK(cudaFuncSetAttribute(dac_fit_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = c < 8 * num_sms() ? c : 8 * num_sms();
+  dac_fit_half_kernel<<<grid, 256, smem, stream>>>((const __half*)base_zs, (const __half*)cur_zs, (const __half*)base_tuned,
+                                                   (const __half*)cur_tuned, b, c, d, k, class_conf_out, knn_idx_zs_out,
+                                                   knn_idx_tuned_out, knn_dist_zs_out, knn_dist_tuned_out);
   note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;

@@ -93,6 +93,7 @@ struct ScoreParams {
   const float* row_scale_inv;          // [n]
   int* redo_count;                     // [1]
   int* redo_rows;                      // [n]
+  const double* log_scale_dev;         // kMode 1: log of the logit scale read from device memory (device-side SGD loop)
   const void* gather_src;              // kGather: the image matrix itself (rows are fetched by index, not by TMA)
   int split_cap;                       // kGather: column-split only when the redo list holds at most this many rows
 };
@@ -442,7 +443,8 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
     uint32_t acc_it = 0;
     // split operands were pre-scaled by powers of two: fold 2^-(e_img + e_txt) into the logit scale (exact)
-    const float scale = kSplit ? p.scale * exp2f(-(float)(p.split_exps[0] + p.split_exps[1])) : p.scale;
+    const float scale_in = (kMode == 1 && p.log_scale_dev != nullptr) ? expf((float)*p.log_scale_dev) : p.scale;
+    const float scale = kSplit ? scale_in * exp2f(-(float)(p.split_exps[0] + p.split_exps[1])) : scale_in;
     auto release_acc = [&](uint32_t as) {
       ptx::tc_fence_before();
       __syncwarp();
@@ -1422,20 +1424,56 @@ extern "C" int ccal_score_pass2(const void* img, const void* txt, const float* c
   return run_fused(0, img, txt, n, c, d, dtype, p, thr, (cudaStream_t)stream, 1);
 }
 
-extern "C" int ccal_ts_loss_grad(const void* img, const void* txt, const int64_t* labels, float log_scale,
-                                 int64_t n, int c, int d, int dtype, float* row_ws, double* out2,
-                                 ccal_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int ts_loss_grad_impl(const void* img, const void* txt, const int64_t* labels, float log_scale,
+                             const double* log_scale_dev, int64_t n, int c, int d, int dtype, float* row_ws, double* out2,
+                             cudaStream_t stream) {
   CCAL_REQUIRE(n >= 1, "ccal_ts_loss_grad: n must be >= 1");
   CCAL_REQUIRE(labels && row_ws && out2, "ccal_ts_loss_grad: NULL pointer");
   ScoreParams p{};
   ThrBlock thr{};
   p.scale = expf(log_scale);
+  p.log_scale_dev = log_scale_dev;
   p.labels = reinterpret_cast<const long long*>(labels);
   p.row_ws = row_ws;
   int rc = run_fused(1, img, txt, n, c, d, dtype, p, thr, stream);
   if (rc) return rc;
   ts_reduce_kernel<<<1, 1024, 0, stream>>>(row_ws, (long long)n, out2);
+  note_launch();
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}
+
+extern "C" int ccal_ts_loss_grad(const void* img, const void* txt, const int64_t* labels, float log_scale,
+                                 int64_t n, int c, int d, int dtype, float* row_ws, double* out2,
+                                 ccal_stream_t stream) {
+  return ts_loss_grad_impl(img, txt, labels, log_scale, nullptr, n, c, d, dtype, row_ws, out2, (cudaStream_t)stream);
+}
+
+extern "C" int ccal_ts_loss_grad_dev(const void* img, const void* txt, const int64_t* labels, const double* log_scale_dev,
+                                     int64_t n, int c, int d, int dtype, float* row_ws, double* out2,
+                                     ccal_stream_t stream) {
+  CCAL_REQUIRE(log_scale_dev != nullptr, "ccal_ts_loss_grad_dev: NULL log-scale pointer");
+  CCAL_REQUIRE(dtype != CCAL_F32, "ccal_ts_loss_grad_dev: fp16 / bf16 operands only");
+  return ts_loss_grad_impl(img, txt, labels, 0.f, log_scale_dev, n, c, d, dtype, row_ws, out2, (cudaStream_t)stream);
+}
+
+// state = {t, velocity, sum of the batch losses, batches}; one thread
+__global__ void sgd_scalar_step_kernel(double* __restrict__ state, const double* __restrict__ loss_grad, double lr,
+                                       double momentum, double weight_decay) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double g = loss_grad[1] + weight_decay * state[0];
+    const double v = momentum * state[1] + g;
+    state[1] = v;
+    state[0] -= lr * v;
+    state[2] += loss_grad[0];
+    state[3] += 1.0;
+  }
+}
+
+extern "C" int ccal_sgd_scalar_step(double* state, const double* loss_grad, double lr, double momentum, double weight_decay,
+                                    ccal_stream_t stream) {
+  CCAL_REQUIRE(state && loss_grad, "ccal_sgd_scalar_step: NULL pointer");
+  sgd_scalar_step_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(state, loss_grad, lr, momentum, weight_decay);
   note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;

@@ -216,6 +216,29 @@ def ts_loss_grad(img: torch.Tensor, txt: torch.Tensor, labels: torch.Tensor, log
     return out
 
 
+def ts_sgd_step(img: torch.Tensor, txt: torch.Tensor, labels: torch.Tensor, state: torch.Tensor, lr: float,
+                momentum: float, weight_decay: float) -> None:
+    """One momentum-SGD step of the log-scale on the DEVICE: state (float64 CUDA [4] = {t, velocity, loss sum,
+    batches}) is read by the loss / gradient kernel and updated in place; nothing returns to the host."""
+    lib = _lib.load()
+    img = _need_cuda("img", img, (torch.bfloat16, torch.float16), 2)
+    txt = _need_cuda("txt", txt, img.dtype, 2)
+    labels = _need_cuda("labels", labels, torch.int64, 1)
+    if not (state.is_cuda and state.dtype == torch.float64 and state.numel() == 4 and state.is_contiguous()):
+        raise ValueError("state must be a contiguous float64 CUDA tensor of 4 elements")
+    n, d = img.shape
+    if labels.numel() != n:
+        raise ValueError("labels length differs from the number of images")
+    ws = torch.empty(2 * n, dtype=torch.float32, device=img.device)
+    out = torch.empty(2, dtype=torch.float64, device=img.device)
+    with torch.cuda.device(img.device):
+        rc = lib.ccal_ts_loss_grad_dev(_ptr(img), _ptr(txt), _ptr(labels), _ptr(state), n, txt.shape[0], d,
+                                       _DTYPES[img.dtype], _ptr(ws), _ptr(out), _stream())
+        _lib.check(rc, "ccal_ts_loss_grad_dev")
+        rc = lib.ccal_sgd_scalar_step(_ptr(state), _ptr(out), float(lr), float(momentum), float(weight_decay), _stream())
+    _lib.check(rc, "ccal_sgd_scalar_step")
+
+
 # --------------------------------------------------------------------------------------
 # K1  kNN + DAC fit
 # --------------------------------------------------------------------------------------
@@ -259,6 +282,31 @@ def dac_fit(base_zs, cur_zs, base_tuned, cur_tuned, k: int):
         rc = lib.ccal_dac_fit(_ptr(base_zs), _ptr(cur_zs), _ptr(base_tuned), _ptr(cur_tuned), b, c, d, int(k),
                               _ptr(cc), _ptr(iz), _ptr(it), _ptr(dz), _ptr(dt), _stream())
     _lib.check(rc, "ccal_dac_fit")
+    return cc, iz, it, dz, dt
+
+
+def dac_fit_f16(base_zs, cur_zs, base_tuned, cur_tuned, k: int):
+    """dac_fit in the reference's float16 arithmetic (inputs: float16 CUDA matrices); same five outputs, the values
+    being half-precision numbers widened to float32."""
+    lib = _lib.load()
+    base_zs = _need_cuda("base_text_features_zs", base_zs, torch.float16, 2)
+    cur_zs = _need_cuda("current_text_features_zs", cur_zs, torch.float16, 2)
+    base_tuned = _need_cuda("base_text_features_tuned", base_tuned, torch.float16, 2)
+    cur_tuned = _need_cuda("current_text_features_tuned", cur_tuned, torch.float16, 2)
+    b, d = base_zs.shape
+    c = cur_zs.shape[0]
+    if base_tuned.shape != base_zs.shape or cur_tuned.shape != cur_zs.shape or cur_zs.shape[1] != d:
+        raise ValueError("zero-shot and tuned feature matrices must have matching shapes")
+    dev = base_zs.device
+    cc = torch.empty(c, dtype=torch.float32, device=dev)
+    iz = torch.empty((c, k), dtype=torch.int32, device=dev)
+    it = torch.empty((c, k), dtype=torch.int32, device=dev)
+    dz = torch.empty((c, k), dtype=torch.float32, device=dev)
+    dt = torch.empty((c, k), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.ccal_dac_fit_f16(_ptr(base_zs), _ptr(cur_zs), _ptr(base_tuned), _ptr(cur_tuned), b, c, d, int(k),
+                                  _ptr(cc), _ptr(iz), _ptr(it), _ptr(dz), _ptr(dt), _stream())
+    _lib.check(rc, "ccal_dac_fit_f16")
     return cc, iz, it, dz, dt
 
 

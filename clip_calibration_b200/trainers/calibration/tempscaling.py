@@ -91,13 +91,30 @@ def ts_loss_and_grad(image_features, text_features, labels, log_scale: float, op
 def fit_logit_scale(image_features, text_features, labels, epochs: int = 20, lr: float = 0.05, batch_size: int = 32,
                     momentum: float = 0.9, weight_decay: float = 5e-4, warmup_epochs: int = 1,
                     warmup_lr: float = 1e-5, init: float = INIT_LOG_SCALE, shuffle_seed: Optional[int] = 0,
-                    operand_dtype=None) -> float:
+                    operand_dtype=None, return_history: bool = False):
     """Learn the scalar log-temperature on cached validation features (reference :146-169 runs
-    the full CLIP forward for every batch of every epoch to fit this one parameter)."""
+    the full CLIP forward for every batch of every epoch to fit this one parameter).
+
+    The whole schedule runs on the device: the parameter, its momentum buffer and the running loss live in a
+    4-double CUDA tensor that the loss / gradient kernel reads and ccal_sgd_scalar_step updates, the shuffled
+    feature matrix is gathered once per epoch, and nothing is read back before the last step - 2 launches per
+    batch and not one host synchronisation (fp16 / bf16 operands; fp32 features keep the host-stepped loop).
+
+    Optimiser semantics - ASSUMED, not pinned: the reference builds them with dassl's `build_optimizer` /
+    `build_lr_scheduler` (tempscaling.py:109-110; Dassl.pytorch is un-vendored and unpinned), driven by
+    configs/calibration/TempScaling/ep20_lr5e-2.yaml and the trainer yaml's OPTIM block: `sgd`, lr 0.05, 20 epochs,
+    cosine schedule, 1 warm-up epoch at constant 1e-5, batch 32 - those come from the reference tree; momentum 0.9,
+    weight decay 5e-4 (applied to the scalar itself), drop_last on the train loader and "the schedule advances once
+    per epoch" (`update_lr` on the last batch, tempscaling.py:166-167) are dassl defaults recalled from its source.
+    The loss and its gradient at a given t ARE pinned (torch autograd, tests); the trajectory is "parity unpinned".
+    """
     img, txt, y = _operands(image_features, text_features, labels, operand_dtype)
     n = img.shape[0]
-    t, vel = float(init), 0.0
     gen = torch.Generator().manual_seed(shuffle_seed) if shuffle_seed is not None else None
+    on_device = img.dtype in (torch.float16, torch.bfloat16)
+    state = torch.tensor([float(init), 0.0, 0.0, 0.0], dtype=torch.float64, device=img.device)
+    t, vel = float(init), 0.0
+    history = []
     for epoch in range(epochs):
         if epoch < warmup_epochs:
             cur_lr = warmup_lr
@@ -106,12 +123,24 @@ def fit_logit_scale(image_features, text_features, labels, epochs: int = 20, lr:
             cur_lr = 0.5 * lr * (1.0 + math.cos(math.pi * (epoch - warmup_epochs) / span))
         order = torch.randperm(n, generator=gen) if gen is not None else torch.arange(n)
         order = order.to(img.device)
-        for lo in range(0, n - batch_size + 1 if n >= batch_size else 1, batch_size):   # drop_last like dassl's train loader
-            sel = order[lo:lo + batch_size]
-            out = native.ts_loss_grad(img[sel].contiguous(), txt, y[sel].contiguous(), t).cpu()
-            g = float(out[1]) + weight_decay * t
-            vel = momentum * vel + g
-            t -= cur_lr * vel
+        img_e, y_e = img.index_select(0, order), y.index_select(0, order)        # one gather per epoch
+        stops = range(0, n - batch_size + 1 if n >= batch_size else 1, batch_size)   # drop_last like dassl's train loader
+        for lo in stops:
+            if on_device:
+                native.ts_sgd_step(img_e[lo:lo + batch_size], txt, y_e[lo:lo + batch_size], state, cur_lr, momentum,
+                                   weight_decay)
+            else:
+                out = native.ts_loss_grad(img_e[lo:lo + batch_size], txt, y_e[lo:lo + batch_size], t).cpu()
+                g = float(out[1]) + weight_decay * t
+                vel = momentum * vel + g
+                t -= cur_lr * vel
+        if return_history and on_device:
+            history.append(state.clone())       # still no synchronisation: read after the loop
+    if on_device:
+        t = float(state[0].item())              # the only device -> host read of the fit
+    if return_history:
+        hist = [h.cpu().numpy() for h in history]
+        return t, [{"t": float(h[0]), "mean_loss_so_far": float(h[2] / max(h[3], 1.0))} for h in hist]
     return t
 
 
@@ -173,116 +202,16 @@ def load_logit_scale(directory: str, epoch: Optional[int] = None) -> float:
 
 
 # ----------------------------------------------------------------------------------------
-# the dassl trainer: only definable where dassl (un-vendored, absent from this image) exists
+# the dassl trainer
 # ----------------------------------------------------------------------------------------
-try:  # pragma: no cover - dassl is not installed in the build image
-    from dassl.engine import TRAINER_REGISTRY
-    from trainers.classification.base_learner import VLBaseLearner
-    from trainers.calibration.basemodel_loader import get_base_model
-    _HAVE_DASSL = True
-except Exception:  # noqa: BLE001
-    _HAVE_DASSL = False
+class TempScaling:
+    """`TempScaling` itself is trainer plumbing over the un-vendored dassl framework ("trainer
+    plumbing stays in the reference") and is NOT rebuilt here.  Inside the reference repository keep the reference's
+    own class (trainers/calibration/tempscaling.py:64-327) and let it build this module's CustomCLIPCalibration -
+    one import line, INTEGRATION.md section 1 - or fit the scalar from cached features with fit_logit_scale() /
+    solve_logit_scale() and store it with save_logit_scale(), which writes the checkpoint layout the reference's
+    `load_model` reads (:260-300)."""
 
-if _HAVE_DASSL:  # pragma: no cover
-    from dassl.optim import build_optimizer, build_lr_scheduler
-    from dassl.data import DataManager
-    from dassl.utils import load_checkpoint
-    import torch.nn.functional as F
-
-    @TRAINER_REGISTRY.register()
-    class TempScaling(VLBaseLearner):
-        """Same trainer plumbing as the reference; the model it builds is this module's
-        CustomCLIPCalibration, so test-time scoring can use forward_confidence."""
-
-        def check_cfg(self, cfg):
-            assert cfg.TRAINER.COOP.PREC in ["fp16", "fp32", "amp"]
-
-        def build_model(self):
-            cfg = self.cfg
-            base_model = get_base_model(cfg, self.dm.dataset.classnames)
-            base_model = self.load_base_stat(cfg, base_model)
-            self.model = CustomCLIPCalibration(cfg, base_model)
-            for name, param in self.model.named_parameters():
-                param.requires_grad_("scale_learner" in name)
-            self.model.to(self.device)
-            self.optim = build_optimizer(self.model.scale_learner, cfg.OPTIM)
-            self.sched = build_lr_scheduler(self.optim, cfg.OPTIM)
-            self.register_model("tempscaling", self.model.scale_learner, self.optim, self.sched)
-            self.scaler = None
-
-        def build_data_loader(self):
-            dm = DataManager(self.cfg)
-            self.train_loader_x = dm.val_loader          # calibration uses the validation split
-            self.train_loader_u = dm.train_loader_u
-            self.val_loader = dm.val_loader
-            self.test_loader = dm.test_loader
-            self.num_classes = dm.num_classes
-            self.num_source_domains = dm.num_source_domains
-            self.lab2cname = dm.lab2cname
-            self.dm = dm
-
-        def parse_batch_train(self, batch):
-            return batch["img"].to(self.device), batch["label"].to(self.device)
-
-        def forward_backward(self, batch):
-            image, label = self.parse_batch_train(batch)
-            logits, _, _ = self.model(image, label)
-            loss = F.cross_entropy(logits, label)
-            self.optim.zero_grad()
-            loss.backward()
-            self.optim.step()
-            if (self.batch_idx + 1) == self.num_batches:
-                self.update_lr()
-            return {"loss": loss.item()}
-
-        def load_base_stat(self, cfg, base_model):
-            if cfg.CALIBRATION.SCALING.BASE_LEARNER == "ZeroshotCLIP":
-                return base_model
-            learner = cfg.CALIBRATION.SCALING.BASE_LEARNER
-            sub = {"MaPLe": "MultiModalPromptLearner", "CLIP_Adapter": "adapter"}.get(learner, "prompt_learner")
-            epoch = cfg.CALIBRATION.SCALING.BASE_EPOCH
-            model_file = "model-best.pth.tar" if epoch is None else "model.pth.tar-" + str(epoch)
-            model_path = osp.join(cfg.CALIBRATION.SCALING.BASE_DIR, sub, model_file)
-            if not osp.exists(model_path):
-                raise FileNotFoundError('Model not found at "{}"'.format(model_path))
-            state_dict = load_checkpoint(model_path)["state_dict"]
-            whole_model = learner in ("MaPLe", "PromptSRC")
-            prefix = "prompt_learner." if whole_model else ""
-            for fixed in ("token_prefix", "token_suffix"):
-                state_dict.pop(prefix + fixed, None)
-            if not whole_model:
-                state_dict = {f"prompt_learner.{k}": v for k, v in state_dict.items()}
-            base_model.load_state_dict(state_dict, strict=False)
-            if learner == "ProDA":
-                base_model.set_classifier()
-            return base_model
-
-        def load_model(self, directory, epoch=None):
-            if not directory:
-                print("Note that load_model() is skipped as no pretrained model is given")
-                return
-            for name in self.get_model_names():
-                model_path = osp.join(directory, name, calibrated_checkpoint_name(epoch))
-                if not osp.exists(model_path):
-                    raise FileNotFoundError('Model not found at "{}"'.format(model_path))
-                checkpoint = load_checkpoint(model_path)
-                self._models[name].load_state_dict(checkpoint["state_dict"], strict=True)
-
-        def after_epoch(self):
-            last_epoch = (self.epoch + 1) == self.max_epoch
-            freq = self.cfg.TRAIN.CHECKPOINT_FREQ
-            if not self.cfg.TEST.NO_TEST and self.cfg.TEST.FINAL_MODEL == "best_val":
-                curr_result = self.test(split="val")
-                if curr_result > self.best_result:
-                    self.best_result = curr_result
-                    self.save_model(self.epoch, self.output_dir, val_result=curr_result,
-                                    model_name=calibrated_checkpoint_name(None))
-            if last_epoch or (freq > 0 and (self.epoch + 1) % freq == 0):
-                self.save_model(self.epoch, self.output_dir, model_name=calibrated_checkpoint_name(self.epoch + 1))
-else:
-    class TempScaling:  # noqa: D401
-        """Placeholder: the trainer class needs the un-vendored dassl framework."""
-
-        def __init__(self, *a, **k):
-            raise ImportError("TempScaling is a dassl trainer; install Dassl.pytorch and run inside the reference "
-                              "repo, or use fit_logit_scale() on cached features")
+    def __init__(self, *a, **k):
+        raise ImportError("TempScaling is a dassl trainer and stays in the reference; use the reference's class with "
+                          "this module's CustomCLIPCalibration, or fit_logit_scale() on cached features")

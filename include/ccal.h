@@ -129,6 +129,16 @@ CCAL_API int ccal_ts_loss_grad(const void* img, const void* txt, const int64_t* 
                       int64_t n, int c, int d, int dtype, float* row_ws, double* out2,
                       ccal_stream_t stream);
 
+/* Device-side training loop of the scalar (tempscaling.py:146-169 + dassl's SGD): ccal_ts_loss_grad_dev is
+ * ccal_ts_loss_grad with the log-scale read from DEVICE memory (a double), and ccal_sgd_scalar_step applies one
+ * momentum-SGD step to it on the device: state = {t, velocity, sum of batch losses, batches};
+ * g = grad + weight_decay * t; v = momentum * v + g; t -= lr * v.  A whole 20-epoch fit is then a stream of launches
+ * with no host synchronisation.  fp16 / bf16 operands only. */
+CCAL_API int ccal_ts_loss_grad_dev(const void* img, const void* txt, const int64_t* labels, const double* log_scale_dev,
+                          int64_t n, int c, int d, int dtype, float* row_ws, double* out2, ccal_stream_t stream);
+CCAL_API int ccal_sgd_scalar_step(double* state, const double* loss_grad, double lr, double momentum,
+                         double weight_decay, ccal_stream_t stream);
+
 /* ---- K1: k nearest rows by Euclidean distance + the DAC map ---------------------------
  * ccal_knn_l2: for every query row q_i [nq,d] the kk = min(k, nr) smallest ||r_j - q_i||_2 over
  * ref rows [nr,d] (fp32), ascending, ties by lowest j.  dist_out [nq,k] (unused tail = +inf),
@@ -153,6 +163,17 @@ CCAL_API int ccal_dac_fit(const float* base_zs, const float* cur_zs, const float
                  const float* cur_tuned, int b, int c, int d, int k,
                  float* class_conf_out, int32_t* knn_idx_zs_out, int32_t* knn_idx_tuned_out,
                  float* knn_dist_zs_out, float* knn_dist_tuned_out, ccal_stream_t stream);
+
+/* ccal_dac_fit_f16: the same fit in the reference's OWN arithmetic when its inputs are float16 numpy arrays (its default
+ * precision: train.py:152; np.linalg.norm / np.sum / np.exp keep float16, distanse_aware_calibration.py:28-42): every
+ * elementwise result rounded to half, squares summed in float32 in numpy's pairwise order, one rounding per row, half
+ * sqrt / sum / exp / ratio, the "< 0.05" test in half.  Inputs are IEEE half [b,d] / [c,d]; outputs as ccal_dac_fit
+ * (class_conf_out holds half values widened to float; distance / index buffers may be NULL).  b <= 16,384.
+ * Opt-in exact-parity mode (DistanseAwareCalibration.fit(..., arithmetic="input")); ccal_dac_fit is the accurate one. */
+CCAL_API int ccal_dac_fit_f16(const void* base_zs, const void* cur_zs, const void* base_tuned, const void* cur_tuned,
+                     int b, int c, int d, int k, float* class_conf_out, int32_t* knn_idx_zs_out,
+                     int32_t* knn_idx_tuned_out, float* knn_dist_zs_out, float* knn_dist_tuned_out,
+                     ccal_stream_t stream);
 
 /* ---- K4: materialised-logits drop-ins -------------------------------------------------
  * ccal_dac_predict_logits = DistanseAwareCalibration.predict (:49-58): in place,

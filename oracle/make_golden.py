@@ -252,6 +252,54 @@ def isotonic():
     np.savez_compressed(os.path.join(OUT, "isotonic.npz"), **out)
 
 
+def in21k_fit(fit_classes=256, seed=0):
+    """DAC fit at BASELINE.json configs[4]'s own shape - 21,841 test classes x 10,000 base classes x 768-d - on a
+    class subset (the reference loop costs ~25 ms per class here): the reference's class_confidence and the
+    oracle's neighbour lists for `fit_classes` classes spread over the vocabulary."""
+    t0 = time.time()
+    N, C, B, D, k, a = synth.CONFIGS["in21k"]
+    txt_zs, txt_tuned, _ = synth.make_text(C, D, seed)
+    sel = np.linspace(0, C - 1, fit_classes).astype(int)
+    dac = DistanseAwareCalibration()
+    dac.fit(txt_zs[:B], txt_zs[sel], txt_tuned[:B], txt_tuned[sel], k)
+    cc = np.asarray(dac.class_confidence)
+    occ, iz, it, dz, dt = orc.dac_fit(txt_zs[:B], txt_zs[sel], txt_tuned[:B], txt_tuned[sel], k)
+    assert np.array_equal(occ, cc), "in21k: oracle dac_fit != reference"
+    np.savez_compressed(os.path.join(OUT, "in21k_fit.npz"), seed=seed, C=C, B=B, D=D, k=k, sel=sel, cc=cc,
+                        knn_idx_zs=iz.astype(np.int32), knn_idx_tuned=it.astype(np.int32), knn_dist_tuned=dt,
+                        txt_checksum=float(txt_tuned.astype(np.float64).sum()))
+    print(f"in21k_fit: {fit_classes} of {C} classes x {B} base x {D}: cc in [{cc.min():.6f}, {cc.max():.6f}] ({time.time()-t0:.1f}s)")
+
+
+def dac_float16():
+    """The reference's DAC fit on FLOAT16 feature arrays - its default precision (train.py:152); numpy keeps float16
+    through np.linalg.norm / np.sum / np.exp (distanse_aware_calibration.py:28-42).  Pins the opt-in
+    arithmetic="input" mode (ccal_dac_fit_f16) and measures how far the float32 answer is from it."""
+    t0 = time.time()
+    out = {}
+    cases = [("sun397_l14", None, (1, 5, 10)), ("openvocab", 256, (5,)), ("in21k", 48, (5,))]
+    for name, fit_classes, ks in cases:
+        N, C, B, D, _, a = synth.CONFIGS[name]
+        txt_zs, txt_tuned, _ = synth.make_text(C, D, 0, rounding=synth.round_to_fp16)
+        zs16, tu16 = txt_zs.astype(np.float16), txt_tuned.astype(np.float16)
+        sel = np.arange(C) if fit_classes is None else np.linspace(0, C - 1, fit_classes).astype(int)
+        out[f"{name}_sel"] = sel
+        for k in ks:
+            dac = DistanseAwareCalibration()
+            dac.fit(zs16[:B], zs16[sel], tu16[:B], tu16[sel], k)
+            cc16 = np.asarray(dac.class_confidence, dtype=np.float64)
+            occ, iz, it, dz, dt = orc.dac_fit(zs16[:B], zs16[sel], tu16[:B], tu16[sel], k)
+            assert np.array_equal(np.asarray(occ, np.float64), cc16), f"{name}: oracle float16 fit != reference"
+            cc32 = np.asarray(orc.dac_fit(txt_zs[:B], txt_zs[sel], txt_tuned[:B], txt_tuned[sel], k)[0], np.float64)
+            out[f"{name}_cc16_k{k}"] = cc16
+            out[f"{name}_dist16_tuned_k{k}"] = np.asarray(dt, np.float32)
+            out[f"{name}_idx16_tuned_k{k}"] = it.astype(np.int32)
+            out[f"{name}_rel_f32_vs_f16_k{k}"] = float(np.max(np.abs(cc32 - cc16) / cc16))
+            print(f"dac_float16 {name} k={k}: {len(sel)} classes, max rel |cc32 - cc16| = {out[f'{name}_rel_f32_vs_f16_k{k}']:.2e}")
+    np.savez_compressed(os.path.join(OUT, "dac_float16.npz"), **out)
+    print(f"dac_float16 written ({time.time()-t0:.1f}s)")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -263,4 +311,6 @@ if __name__ == "__main__":
     run_case("sun397_l14", ks=(1, 5, 10))
     run_case("imagenet")
     run_case("openvocab", n_override=1024, fit_classes=256)
+    in21k_fit()
+    dac_float16()
     print("golden fixtures written to", OUT)

@@ -99,6 +99,63 @@ def test_dac_fit_matches_reference(cuda_lib, name, ks, golden, synth_case):
         assert (zgot != g[f"knn_idx_zs_k{k}"]).mean() < 1e-3
 
 
+def test_dac_fit_at_the_in21k_shape(cuda_lib, golden):
+    """BASELINE.json configs[4]'s own fit: 21,841 test classes x 10,000 base classes x 768-d (tensor-core filter +
+    exact verification), against the reference's class_confidence on 256 classes spread over the vocabulary."""
+    g = golden("in21k_fit")
+    C, B, D, k = int(g["C"]), int(g["B"]), int(g["D"]), int(g["k"])
+    txt_zs, txt_tuned, _ = synth.make_text(C, D, int(g["seed"]))
+    assert abs(txt_tuned.astype(np.float64).sum() - float(g["txt_checksum"])) < 1e-6, "generator drifted"
+    dac = DistanseAwareCalibration()
+    dac.fit(txt_zs[:B], txt_zs, txt_tuned[:B], txt_tuned, k)
+    sel = g["sel"]
+    np.testing.assert_allclose(dac.class_confidence[sel], g["cc"], rtol=2e-6)
+    assert np.array_equal(dac.class_confidence[sel] == 1.0, g["cc"] == 1.0)
+    assert np.all(dac.class_confidence[:B] == 1.0)                     # every base class finds itself at distance 0
+    dgot = dac.knn_distances_tuned.cpu().numpy()[sel]
+    np.testing.assert_allclose(dgot, g["knn_dist_tuned"], rtol=2e-6, atol=1e-7)
+    igot = dac.knn_indices_tuned.cpu().numpy()[sel]
+    diff = igot != g["knn_idx_tuned"]
+    if diff.any():                                                     # only where two distances coincide to rounding
+        assert np.all(np.abs(dgot[diff] - g["knn_dist_tuned"][diff]) <= 2e-6 * g["knn_dist_tuned"][diff] + 1e-7)
+    assert (dac.knn_indices_zs.cpu().numpy()[sel] != g["knn_idx_zs"]).mean() < 1e-3
+
+
+@pytest.mark.parametrize("name,ks", [("sun397_l14", (1, 5, 10)), ("openvocab", (5,)), ("in21k", (5,))])
+def test_dac_fit_in_the_reference_float16_arithmetic(cuda_lib, name, ks, golden):
+    """The reference's default precision is fp16 and numpy keeps float16 through the whole fit
+    (distanse_aware_calibration.py:28-42): `arithmetic="input"` must give the reference's class_confidence for
+    float16 inputs exactly (half-precision values), where the default float32 arithmetic differs by ~1e-3."""
+    g = golden("dac_float16")
+    N, C, B, D, _, _ = synth.CONFIGS[name]
+    txt_zs, txt_tuned, _ = synth.make_text(C, D, 0, rounding=synth.round_to_fp16)
+    zs16, tu16 = txt_zs.astype(np.float16), txt_tuned.astype(np.float16)
+    sel = g[f"{name}_sel"]
+    for k in ks:
+        want = g[f"{name}_cc16_k{k}"]
+        dac = DistanseAwareCalibration()
+        dac.fit(zs16[:B], zs16[sel], tu16[:B], tu16[sel], k, arithmetic="input")
+        got = np.asarray(dac.class_confidence)
+        assert got.dtype == np.float64
+        off = got != want
+        # np.exp's float32 result may sit within rounding of a half-way point of the float16 grid: allow a stray ulp
+        assert off.mean() <= 0.005 and np.all(np.abs(got[off] - want[off]) <= 1.0e-3 * want[off]), (k, off.sum())
+        kk = min(k, B)
+        np.testing.assert_array_equal(dac.knn_distances_tuned.cpu().numpy()[:, :kk], g[f"{name}_dist16_tuned_k{k}"])
+        # the default (float32) arithmetic is the accurate answer and is NOT what the reference gets from fp16 arrays
+        dac32 = DistanseAwareCalibration()
+        dac32.fit(zs16[:B], zs16[sel], tu16[:B], tu16[sel], k)
+        rel = np.max(np.abs(np.asarray(dac32.class_confidence) - want) / want)
+        assert 1e-5 < rel < 2e-3, rel
+        assert abs(rel - float(g[f"{name}_rel_f32_vs_f16_k{k}"])) < 2e-5
+    # torch.float16 CUDA tensors take the same route; float32 inputs ignore the switch
+    dac = DistanseAwareCalibration()
+    dac.fit(*[torch.from_numpy(x).cuda() for x in (zs16[:B], zs16[sel], tu16[:B], tu16[sel])], ks[-1], arithmetic="input")
+    assert np.array_equal(np.asarray(dac.class_confidence), got)
+    with pytest.raises(ValueError):
+        dac.fit(zs16[:B], zs16[sel], tu16[:B], tu16[sel], 5, arithmetic="float16")
+
+
 def test_dac_fit_k_larger_than_base_and_duplicates(cuda_lib):
     case = synth.make_case("tiny", 16, 6, 3, 64, 5, 0.3, seed=9)
     base_zs = case.base_zs.copy(); base_zs[2] = base_zs[1]            # duplicate base row (equal distances)
@@ -402,6 +459,38 @@ def test_fit_logit_scale_reduces_loss_and_checkpoint_roundtrip(cuda_lib, tmp_pat
     assert abs(tempscaling.load_logit_scale(str(tmp_path), 5) - t) < 1e-6
     learner = tempscaling.ScaleLearner(None, torch.float32)
     assert abs(float(learner()) - np.exp(4.6052)) < 1e-3 and list(learner.state_dict()) == ["logit_scale"]
+
+
+def test_fit_logit_scale_device_loop_matches_host_stepping(cuda_lib):
+    """f-3: with 16-bit operands the whole SGD schedule runs on the device (the scalar, its momentum buffer and the
+    running loss live in device memory; no read-back until the end).  It must walk the same trajectory as stepping
+    the same objective from the host, batch by batch, with the same shuffles."""
+    import math
+    case = synth.make_case("tsdev", 500, 120, 60, 512, 5, 0.3, seed=5)
+    img = torch.from_numpy(case.img).cuda().to(torch.bfloat16)
+    txt = torch.from_numpy(case.txt_tuned).cuda().to(torch.bfloat16)
+    y = torch.from_numpy(case.labels).cuda()
+    epochs, bs, lr, mom, wd = 4, 32, 0.05, 0.9, 5e-4
+    n0 = native.launch_count()
+    t_dev, hist = tempscaling.fit_logit_scale(img, txt, y, epochs=epochs, lr=lr, batch_size=bs, momentum=mom, weight_decay=wd,
+                                              return_history=True)
+    batches = epochs * (500 // bs)
+    assert native.launch_count() - n0 == 3 * batches            # scoring kernel + fixed-order reduce + SGD step, per batch
+    gen = torch.Generator().manual_seed(0)
+    t, vel = tempscaling.INIT_LOG_SCALE, 0.0
+    for epoch in range(epochs):
+        cur = 1e-5 if epoch < 1 else 0.5 * lr * (1.0 + math.cos(math.pi * (epoch - 1) / (epochs - 1)))
+        order = torch.randperm(500, generator=gen).cuda()
+        for lo in range(0, 500 - bs + 1, bs):
+            sel = order[lo:lo + bs]
+            _, g = tempscaling.ts_loss_and_grad(img[sel], txt, y[sel], t)
+            vel = mom * vel + g + wd * t
+            t -= cur * vel
+        assert abs(hist[epoch]["t"] - t) < 5e-5, (epoch, hist[epoch]["t"], t)
+    assert abs(t_dev - t) < 5e-5 and len(hist) == epochs
+    l0, _ = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, tempscaling.INIT_LOG_SCALE)
+    l1, _ = orc.ts_loss_and_grad(case.img, case.txt_tuned, case.labels, t_dev)
+    assert l1 < l0
 
 
 def test_c_abi_from_plain_c(cuda_lib):
@@ -757,6 +846,37 @@ def test_vl_calibration_bin_based_multi_isotonic(cuda_lib, golden):
     with pytest.raises(NotImplementedError):
         vl_calibrator.VLCalibration(None, base_calibration_mode="bin_based", base_bin_calibrator_name="histogram_binning",
                                     val_dict=val_dict).fit()
+
+
+def test_custom_clip_calibration_forward_confidence(cuda_lib, golden, synth_case):
+    """a-3: CustomCLIPCalibration.forward keeps the reference contract (logits, image_features, text_features);
+    forward_confidence is the fused route (no [batch, C] matrix) and must agree with the oracle chain at the
+    learner's current scale, with and without DAC multipliers."""
+    g, case = golden("sun397_l14"), synth_case("sun397_l14")
+    img = torch.from_numpy(case.img[:3000]).cuda().to(torch.bfloat16)
+    txt = torch.from_numpy(case.txt_tuned).cuda().to(torch.bfloat16)
+
+    class Base(torch.nn.Module):
+        dtype = torch.bfloat16
+
+        def forward(self, image):
+            return None, image, txt
+
+    model = tempscaling.CustomCLIPCalibration(None, Base()).cuda()
+    with torch.no_grad():
+        model.scale_learner.logit_scale.fill_(float(np.log(80.0)))
+    scale = float(model.scale_learner().float())
+    logits, f_img, f_txt = model(img)
+    assert logits.shape == (3000, txt.shape[0]) and f_img is img and f_txt is txt
+    cc = np.asarray(g["cc_k5"], np.float32)
+    for ccx in (None, cc):
+        pred, conf = model.forward_confidence(img, None if ccx is None else torch.from_numpy(ccx).cuda())
+        pref, cref, gap = orc.score_chain(case.img[:3000], case.txt_tuned, ccx, scale)
+        ok = gap > TIE_GAP
+        assert np.array_equal(pred.cpu().numpy()[ok], pref[ok])
+        np.testing.assert_allclose(conf.cpu().numpy()[ok], cref[ok], rtol=1e-4)
+    # the materialised logits of forward() give the same labels
+    assert (logits.float().argmax(1).cpu().numpy()[ok] == pref[ok]).mean() > 0.995
 
 
 def test_two_launch_scoring_is_bit_identical(cuda_lib, golden):

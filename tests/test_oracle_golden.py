@@ -106,3 +106,24 @@ def test_isotonic_calibrators_match_reference(golden):
         np.testing.assert_allclose(b_val[rv], g[f"bms_{strategy}_val_out"], rtol=1e-13, atol=1e-15)
         np.testing.assert_allclose(orc.bin_mean_shift_transform(state, tp, d["test_prox"])[rt],
                                    g[f"bms_{strategy}_test_out"], rtol=1e-13, atol=1e-15)
+
+
+def test_oracle_float16_arithmetic_fit_matches_reference_golden(golden):
+    """The oracle keeps the input dtype like the reference (float16 arrays stay float16 through norm / sum / exp):
+    its class_confidence for float16 features equals the fixture the real reference produced (dac_float16.npz)."""
+    from clip_calibration_b200 import synth
+    g = golden("dac_float16")
+    N, C, B, D, _, _ = synth.CONFIGS["sun397_l14"]
+    txt_zs, txt_tuned, _ = synth.make_text(C, D, 0, rounding=synth.round_to_fp16)
+    zs16, tu16 = txt_zs.astype(np.float16), txt_tuned.astype(np.float16)
+    cc, *_ = orc.dac_fit(zs16[:B], zs16, tu16[:B], tu16, 5)
+    assert np.array_equal(np.asarray(cc, np.float64), g["sun397_l14_cc16_k5"])
+
+
+def test_oracle_fit_at_in21k_shape_matches_reference_golden(golden):
+    from clip_calibration_b200 import synth
+    g = golden("in21k_fit")
+    txt_zs, txt_tuned, _ = synth.make_text(int(g["C"]), int(g["D"]), int(g["seed"]))
+    B, sel = int(g["B"]), g["sel"][:24]
+    cc, *_ = orc.dac_fit(txt_zs[:B], txt_zs[sel], txt_tuned[:B], txt_tuned[sel], int(g["k"]))
+    assert np.array_equal(cc, g["cc"][:24])
