@@ -472,7 +472,7 @@ def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2
         del img
         torch.cuda.empty_cache()
         e2e_table = {}
-        chunk_rows = 131072 if n_images > 2 * 131072 else max(1024, -(-n_images // 4 // 128) * 128)
+        chunk_rows = 262144 if n_images > 2 * 262144 else max(1024, -(-n_images // 4 // 128) * 128)
 
         def e2e_step():
             # H2D of the four text matrices + DAC fit (class_confidence stays on the device); with several ranks the

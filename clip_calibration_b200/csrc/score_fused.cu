@@ -119,9 +119,9 @@ __device__ __forceinline__ void max_chunk(const uint32_t (&raw)[32], int nv, int
   }
 }
 
+// Returns the chunk's partial sum of 2^(a2 x - b2) (the caller adds it to the tile's running sum).
 template <bool kMasked, int kMode>
-__device__ __forceinline__ void exp_chunk(const uint32_t (&raw)[32], int nv, float a2, float b2, float& sum,
-                                          float& wsum) {
+__device__ __forceinline__ float exp_chunk(const uint32_t (&raw)[32], int nv, float a2, float b2, float& wsum) {
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, w0 = 0.f, w1 = 0.f;
   if constexpr (!kMasked && kMode == 0) {
     // full chunk, confidence only: the scale-and-shift and the four partial sums run as packed fp32 pairs
@@ -140,8 +140,7 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&raw)[32], int nv, flo
     }
     ptx::unpack2(s01, s0, s1);
     ptx::unpack2(s23, s2, s3);
-    sum += (s0 + s1) + (s2 + s3);
-    return;
+    return (s0 + s1) + (s2 + s3);
   }
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -159,9 +158,15 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&raw)[32], int nv, flo
   }
   // chunk partial first, then into the running total: two-level summation keeps the
   // rounding error of a 49k-term sum at the ~1e-6 level
-  sum += (s0 + s1) + (s2 + s3);
   if (kMode == 1) wsum += w0 + w1;
+  return (s0 + s1) + (s2 + s3);
 }
+
+// Verify pass: a chunk can hold the row maximum only if one of its terms 2^(a2 (x - m)) reaches 1 (m = the guessed
+// class's exact logit, itself one of the row's logits) - so only chunks whose partial sum is at least this close
+// to 1 are searched for the exact maximum / first argmax.  Skipped chunks hold logits strictly below m (by more
+// than 0.01 / a2, far beyond any rounding), and the guessed class's own chunk always qualifies.
+constexpr float kMaxSearchThreshold = 0.99f;
 
 // kCtas = 1: one CTA per 128-row image tile (tcgen05 cta_group::1).
 // kCtas = 2: a CTA PAIR (2-CTA cluster, cta_group::2) per 256-row tile: each CTA keeps its own 128 image
@@ -317,22 +322,39 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
               // stored where TMA's 128-byte swizzle would have put them (chunk index XOR row % 8)
               unsigned char* slab = op_ptr + (size_t)kb * kASlabBytes;
               const unsigned char* src = reinterpret_cast<const unsigned char*>(p.gather_src);
-#pragma unroll 2
+              if (kb == 0) {
+                // pull the rows of this CTA's NEXT unit towards L2 while the current one is being scored
+                const int un = u + n_units;
+                if (un < n_work) {
+                  const int next_row0 = (un / S) * kTileRows + (int)rank * kBlockM;
+                  for (int r = lane; r < kBlockM; r += 32) {
+                    const int ns = next_row0 + r;
+                    if (ns < n_listed) {
+                      const unsigned char* gp = src + (size_t)p.redo_rows[ns] * (size_t)p.d * 2;
+                      for (int off = 0; off < p.d * 2; off += 128) ptx::prefetch_l2(gp + off);
+                    }
+                  }
+                }
+              }
+              uint4 v[kBlockM / 32][8];                     // the whole slab's loads in flight before the first store
+#pragma unroll
               for (int rr = 0; rr < kBlockM / 32; ++rr) {
-                const int r = rr * 32 + lane;
-                const int slot = row0 + r;
-                uint4 v[8];
+                const int slot = row0 + rr * 32 + lane;
                 if (slot < n_listed) {
                   const uint4* g = reinterpret_cast<const uint4*>(src + (size_t)p.redo_rows[slot] * (size_t)p.d * 2 + (size_t)kb * 128);
 #pragma unroll
-                  for (int q = 0; q < 8; ++q) v[q] = __ldg(g + q);
+                  for (int q = 0; q < 8; ++q) v[rr][q] = __ldg(g + q);
                 } else {
 #pragma unroll
-                  for (int q = 0; q < 8; ++q) v[q] = make_uint4(0u, 0u, 0u, 0u);
+                  for (int q = 0; q < 8; ++q) v[rr][q] = make_uint4(0u, 0u, 0u, 0u);
                 }
+              }
+#pragma unroll
+              for (int rr = 0; rr < kBlockM / 32; ++rr) {
+                const int r = rr * 32 + lane;
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                  *reinterpret_cast<uint4*>(slab + r * 128 + ((q ^ (r & 7)) << 4)) = v[q];
+                  *reinterpret_cast<uint4*>(slab + r * 128 + ((q ^ (r & 7)) << 4)) = v[rr][q];
               }
               ptx::fence_proxy_async_smem();
               __syncwarp();
@@ -526,8 +548,9 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
             uint32_t raw[32];
             ptx::tmem_ld_32x32(tmem_base + lane_sel + as * kBlockN + ch * 32, raw);
             ptx::tmem_ld_wait(raw);
-            exp_chunk<false, 0>(raw, 32, a2, b2, tile_sum, wsum);
-            if (kMode == 2) max_chunk<false>(raw, 32, nt * kBlockN + ch * 32, xm, xarg);
+            const float part = exp_chunk<false, 0>(raw, 32, a2, b2, wsum);
+            tile_sum += part;
+            if (kMode == 2 && !(part < kMaxSearchThreshold)) max_chunk<false>(raw, 32, nt * kBlockN + ch * 32, xm, xarg);
           }
         } else
         for (int ch = 0; ch * 32 < valid; ++ch) {
@@ -535,9 +558,10 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
           ptx::tmem_ld_32x32(tmem_base + lane_sel + as * kBlockN + ch * 32, raw);
           ptx::tmem_ld_wait(raw);
           const int nv = valid - ch * 32;
-          if (nv >= 32) exp_chunk<false, kMode == 1 ? 1 : 0>(raw, 32, a2, b2, tile_sum, wsum);
-          else exp_chunk<true, kMode == 1 ? 1 : 0>(raw, nv, a2, b2, tile_sum, wsum);
-          if (kMode == 2) {
+          const float part = (nv >= 32) ? exp_chunk<false, kMode == 1 ? 1 : 0>(raw, 32, a2, b2, wsum)
+                                        : exp_chunk<true, kMode == 1 ? 1 : 0>(raw, nv, a2, b2, wsum);
+          tile_sum += part;
+          if (kMode == 2 && !(part < kMaxSearchThreshold)) {
             if (nv >= 32) max_chunk<false>(raw, 32, nt * kBlockN + ch * 32, xm, xarg);
             else max_chunk<true>(raw, nv, nt * kBlockN + ch * 32, xm, xarg);
           }

@@ -64,6 +64,31 @@ def _side_stream(device: torch.device) -> torch.cuda.Stream:
     return _SIDE_STREAMS[key]
 
 
+_STAGING = {}
+
+
+def _staging(device: torch.device, rows: int, d: int, dtype, tag: str = "ring") -> dict:
+    """Device staging buffers of accumulate_host, kept per (device, shape): two [rows, d] feature buffers + label
+    buffers with their `copied` / `consumed` events.  Because they persist, a new call only has to wait for the
+    previous user of the SAME buffer (its `consumed` event) instead of ordering its copies after everything on the
+    compute stream."""
+    key = (device.type, device.index, int(rows), int(d), dtype, tag)
+    st = _STAGING.get(key)
+    if st is None:
+        if len(_STAGING) > 8:                      # shapes changed: drop the old buffers
+            _STAGING.clear()
+        n_buf = 2 if tag == "ring" else 1
+        st = {"bufs": [torch.empty((rows, d), dtype=dtype, device=device) for _ in range(n_buf)],
+              "lbufs": [torch.empty(rows, dtype=torch.int64, device=device) for _ in range(n_buf)],
+              "copied": [torch.cuda.Event() for _ in range(n_buf)],
+              "consumed": [torch.cuda.Event() for _ in range(n_buf)]}
+        cur = torch.cuda.current_stream(device)
+        for ev in st["consumed"]:
+            ev.record(cur)                         # allocation (and any earlier use of that memory) precedes the first copy
+        _STAGING[key] = st
+    return st
+
+
 _COPY_STREAMS = {}
 
 
@@ -252,9 +277,11 @@ class CalibratedScorer:
         """End-to-end path for HOST inputs (ideally pinned): the shard is cut into row chunks,
         chunk i+1 is copied host->device on a side stream while chunk i is being scored, and
         only the bin table (and optionally pred/conf) ever comes back.  With `ramp` the first chunks
-        are small (1/8, 1/4, 1/2 of chunk_rows) so scoring starts after a few MB have arrived instead
+        are small (16k rows, doubling up to chunk_rows) so scoring starts after a few MB have arrived instead
         of after a full chunk - the un-overlapped head of the pipeline is what 8 ranks sharing one
-        host's memory bandwidth feel most."""
+        host's memory bandwidth feel most.  The device staging buffers are kept per (device, shape) and are ordered
+        by their own events, so the first copies do not wait for whatever else is queued on the compute stream
+        (another rank's text upload + broadcast, the DAC fit)."""
         if image_features.is_cuda:
             raise ValueError("accumulate_host expects host tensors; use score() for device tensors")
         if image_features.dtype != self.operand_dtype:
@@ -266,31 +293,36 @@ class CalibratedScorer:
             self._copy_stream = _copy_stream(self.device)
         copy = self._copy_stream
         chunk_rows = max(128, min(int(chunk_rows), n))
-        bufs = [torch.empty((chunk_rows, d), dtype=self.operand_dtype, device=self.device) for _ in range(2)]
-        lbufs = [torch.empty(chunk_rows, dtype=torch.int64, device=self.device) for _ in range(2)]
-        copied = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
-        preds, confs = [], []
-        copy.wait_stream(comp)
         bounds, lo = [], 0
-        sizes = [chunk_rows // 8, chunk_rows // 4, chunk_rows // 2] if ramp and n > 2 * chunk_rows else []
+        sizes = []
+        if ramp and n > chunk_rows:
+            step = min(16384, chunk_rows // 2)
+            while step < chunk_rows and sum(sizes) + step < n - chunk_rows // 2:
+                sizes.append(step)
+                step *= 2
         while lo < n:
             step = max(128, sizes.pop(0)) if sizes else chunk_rows
             bounds.append((lo, min(n, lo + step)))
             lo += step
         want_out = keep_outputs or self.keep_outputs
+        preds, confs = [], []
+        stage = _staging(self.device, chunk_rows, d, self.operand_dtype)
+        bufs, lbufs, copied, consumed = stage["bufs"], stage["lbufs"], stage["copied"], stage["consumed"]
         if self._fit_done is not None and len(bounds) > 3 and self.operand_dtype in (torch.float16, torch.bfloat16):
             # The DAC fit is still running on its side stream (from_dac(overlap_fit=True)).  Pass 1 needs no
             # multipliers: run it on the head chunks as they arrive, underneath the fit and its uploads, then wait
             # for the fit and finish the head with ONE pass-2 launch.  Same results as the fused launch, bit for bit.
-            head, bounds = bounds[:3], bounds[3:]
+            n_head = 3
+            head, bounds = bounds[:n_head], bounds[n_head:]
             head_rows = head[-1][1]
-            hbuf = torch.empty((head_rows, d), dtype=self.operand_dtype, device=self.device)
-            hlab = torch.empty(head_rows, dtype=torch.int64, device=self.device)
+            hstage = _staging(self.device, head_rows, d, self.operand_dtype, tag="head")
+            hbuf, hlab = hstage["bufs"][0], hstage["lbufs"][0]
             parts = []
             for j, (lo, hi) in enumerate(head):
                 arrived = torch.cuda.Event()
                 with torch.cuda.stream(copy):
+                    if j == 0:
+                        copy.wait_event(hstage["consumed"][0])       # the previous call's pass 2 has read the buffer
                     hbuf[lo:hi].copy_(image_features[lo:hi], non_blocking=True)
                     hlab[lo:hi].copy_(labels[lo:hi], non_blocking=True)
                     arrived.record(copy)
@@ -302,12 +334,11 @@ class CalibratedScorer:
             dotmax = torch.cat([q[0] for q in parts])
             pred = torch.cat([q[1] for q in parts])
             self._await_fit()
-            conf = native.score_pass2(hbuf, self.txt, dotmax, pred, self.class_conf, self.logit_scale, hlab,
-                                      self.thresholds, self.table, want_conf=want_out)
-            hbuf.record_stream(copy)
-            hlab.record_stream(copy)
+            conf = native.score_pass2(hbuf[:head_rows], self.txt, dotmax, pred, self.class_conf, self.logit_scale,
+                                      hlab[:head_rows], self.thresholds, self.table, want_conf=want_out)
             if self.keep_outputs:
-                self._keep(pred, conf, hlab)
+                self._keep(pred, conf, hlab[:head_rows].clone())
+            hstage["consumed"][0].record(comp)
             if keep_outputs:
                 preds.append(pred)
                 confs.append(conf)
@@ -315,16 +346,14 @@ class CalibratedScorer:
         for i, (lo, hi) in enumerate(bounds):
             b = i & 1
             with torch.cuda.stream(copy):
-                if i >= 2:
-                    copy.wait_event(consumed[b])
+                copy.wait_event(consumed[b])                         # (recorded at creation / by the previous user)
                 bufs[b][: hi - lo].copy_(image_features[lo:hi], non_blocking=True)
                 lbufs[b][: hi - lo].copy_(labels[lo:hi], non_blocking=True)
                 copied[b].record(copy)
             comp.wait_event(copied[b])
             pred, conf, _ = native.score_fused(bufs[b][: hi - lo], self.txt, self.class_conf, self.logit_scale,
                                                lbufs[b][: hi - lo], self.thresholds, self.table,
-                                               want_pred=keep_outputs or self.keep_outputs,
-                                               want_conf=keep_outputs or self.keep_outputs)
+                                               want_pred=want_out, want_conf=want_out)
             if self.keep_outputs:
                 self._keep(pred, conf, lbufs[b][: hi - lo].clone())
             consumed[b].record(comp)
