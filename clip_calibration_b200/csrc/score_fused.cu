@@ -410,7 +410,7 @@ score_fused_kernel(const __grid_constant__ CUtensorMap map_img, const __grid_con
           for (int nt = nt_begin; nt < nt_end; ++nt, ++acc_it) {
             const uint32_t as = acc_it & 1u;
             const uint32_t aph = (acc_it >> 1) & 1u;
-            ptx::mbar_wait(&ctl->tmem_empty[as], aph ^ 1u);      // epilogue(s) have drained this stage
+            ptx::mbar_wait_short(&ctl->tmem_empty[as], aph ^ 1u);      // epilogue(s) have drained this stage
             ptx::tc_fence_after();
             const uint32_t d_tmem = tmem_base + as * kBlockN;
             const bool first_use_of_a = kResident && pass == p.pass_lo && nt == nt_begin;

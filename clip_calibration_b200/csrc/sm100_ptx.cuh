@@ -86,6 +86,30 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t p
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(smem_u32(bar), parity);
 }
+// Same contract without the long suspend hint: for barriers completed by plain mbarrier.arrive from other warps /
+// the peer CTA (accumulator-stage release), where a sleeping waiter was seen to wake late.
+__device__ __forceinline__ void mbar_wait_short(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 4095u) != 0) continue;
+    const uint64_t now = globaltimer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000ull) {
+      printf("ccal: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
 
 // ---------------------------------------------------------------- TMA
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
@@ -210,16 +234,21 @@ __device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar, uint3
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint64_t t0 = 0;
+  uint32_t spins = 0;
   for (;;) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (ok) return;
+    // no suspend-time hint here: this barrier is completed by plain mbarrier.arrive from producer threads (not by
+    // TMA / tcgen05.commit), and with the 20 us hint the waiter was observed to sleep out the whole hint per slab
+    // (ncu r02d: 112 us of waiting per 128-row gather)
+    if ((++spins & 1023u) != 0) continue;
     const uint64_t now = globaltimer_ns();
     if (t0 == 0) t0 = now;
     else if (now - t0 > 4000000000ull) {

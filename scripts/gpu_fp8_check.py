@@ -114,8 +114,10 @@ def main():
         img, txt, labels, cc = make(n, c, d, a, b)
         t_old = timed("0", img, txt, labels, cc, thr)
         native.score_guess_stats(reset=True)
+        native.score_trace(reset=True)
         t_new = timed("1", img, txt, labels, cc, thr)
         rows, redone = native.score_guess_stats(reset=True)
+        emit(trace=name, kernels=native.score_trace(reset=True))
         flops = 2.0 * n * c * d
         emit(timing=name, two_pass_ms=t_old, guess_verify_ms=t_new, speedup=sum(t_old) / sum(t_new),
              algorithmic_tflops=[flops / (sum(t_old) / len(t_old) * 1e-3) / 1e12, flops / (sum(t_new) / len(t_new) * 1e-3) / 1e12],
