@@ -48,6 +48,14 @@ def evaluate_pred_conf(preds, confs, labels, ece_bins: int = 10, piece_bins: int
 def evaluate(probs, labels, text_proximity=None, ece_bins: int = 10, piece_bins: int = 10):
     """Reference signature: a full probability matrix in, the result dict out."""
     p = probs if isinstance(probs, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(probs))
-    p = p.to(device="cuda", dtype=torch.float32).contiguous()
-    pred, conf = native.row_argmax(p)              # preds = argmax(probs), confs = probs[i, preds_i]
+    if p.dtype == torch.float64:
+        # calibrated probabilities (isotonic / density-ratio outputs) are float64 and may differ below float32
+        # resolution: keep them - first argmax and its float64 value (torch: first maximal index), float64 binning
+        p = p.to(device="cuda").contiguous()
+        pred = torch.argmax(p, dim=1)
+        conf = p.gather(1, pred[:, None])[:, 0].contiguous()
+        pred = pred.to(torch.int32)
+    else:
+        p = p.to(device="cuda", dtype=torch.float32).contiguous()
+        pred, conf = native.row_argmax(p)          # preds = argmax(probs), confs = probs[i, preds_i]
     return evaluate_pred_conf(pred, conf, labels, ece_bins, piece_bins, text_proximity, n_classes=p.shape[1])

@@ -542,11 +542,10 @@ def radix_hist(keys: torch.Tensor, level: int, prefixes: Optional[Sequence[int]]
     return hist
 
 
-def order_statistics(keys: torch.Tensor, ranks: Sequence[int], group=None) -> np.ndarray:
-    """Exact values of the given 0-based ranks of the (globally sorted, non-negative) float32
-    keys.  Two 16-bit radix-histogram passes on the device; with `group` the histograms are
-    summed over ranks (torch.distributed all-reduce) so every rank gets the global answer."""
-    keys = _need_cuda("keys", keys, torch.float32, 1)
+def _order_statistics_bits(keys: torch.Tensor, ranks: Sequence[int], group=None):
+    """(bit patterns uint32 [len(ranks)], number of keys strictly below each of them) for the given 0-based ranks of
+    the globally sorted 32-bit keys (compared as unsigned bit patterns; `keys` is any 4-byte CUDA tensor viewed as
+    float32).  Two 16-bit radix-histogram passes on the device, all-reduced over `group`."""
     h0 = radix_hist(keys, 0)
     if group is not None:
         torch.distributed.all_reduce(h0, group=group)
@@ -557,7 +556,8 @@ def order_statistics(keys: torch.Tensor, ranks: Sequence[int], group=None) -> np
         raise ValueError("rank out of range")
     hi = np.searchsorted(c0, np.asarray(ranks), side="right")          # bucket holding each rank
     uniq = sorted(set(int(h) for h in hi))
-    out = np.empty(len(ranks), np.float32)
+    bits = np.empty(len(ranks), np.uint32)
+    below = np.empty(len(ranks), np.int64)
     for lo in range(0, len(uniq), 64):
         part = uniq[lo:lo + 64]
         h1 = radix_hist(keys, 1, part)
@@ -569,5 +569,37 @@ def order_statistics(keys: torch.Tensor, ranks: Sequence[int], group=None) -> np
                 row = part.index(int(hi[j]))
                 before = int(c0[hi[j] - 1]) if hi[j] > 0 else 0
                 low = int(np.searchsorted(c1[row], r - before, side="right"))
-                out[j] = np.array([(int(hi[j]) << 16) | low], np.uint32).view(np.float32)[0]
-    return out
+                bits[j] = (int(hi[j]) << 16) | low
+                below[j] = before + (int(c1[row][low - 1]) if low > 0 else 0)
+    return bits, below
+
+
+def order_statistics(keys: torch.Tensor, ranks: Sequence[int], group=None) -> np.ndarray:
+    """Exact values of the given 0-based ranks of the (globally sorted, non-negative) float32 or float64
+    keys.  Two 16-bit radix-histogram passes on the device per 32 key bits; with `group` the histograms are
+    summed over ranks (torch.distributed all-reduce) so every rank gets the global answer."""
+    if keys.dtype == torch.float64:
+        return _order_statistics_f64(keys, ranks, group)
+    keys = _need_cuda("keys", keys, torch.float32, 1)
+    bits, _ = _order_statistics_bits(keys, ranks, group)
+    return bits.view(np.float32)
+
+
+def _order_statistics_f64(keys: torch.Tensor, ranks: Sequence[int], group=None) -> np.ndarray:
+    """float64 keys (calibrated confidences: isotonic / density-ratio outputs are float64 and differ from each other
+    far below float32 resolution): the order statistic's upper 32 bits are located first, then its lower 32 bits
+    among the keys that share them - the same radix kernels on each half, so the edges are exact in float64."""
+    keys = _need_cuda("keys", keys, torch.float64, 1)
+    b64 = keys.view(torch.int64)
+    hi = (b64 >> 32).to(torch.int32)
+    lo = (b64 & 0xFFFFFFFF).to(torch.int32)                      # wraps: the bit pattern is what the kernels read
+    ranks = [int(r) for r in ranks]
+    hbits, hbelow = _order_statistics_bits(hi.view(torch.float32), ranks, group)
+    out = np.empty(len(ranks), np.uint64)
+    for h in sorted(set(int(x) for x in hbits)):
+        js = [j for j in range(len(ranks)) if int(hbits[j]) == h]
+        sub = lo[hi == int(np.int32(np.uint32(h)))].contiguous()
+        lbits, _ = _order_statistics_bits(sub.view(torch.float32), [ranks[j] - int(hbelow[j]) for j in js], group)
+        for j, lb in zip(js, lbits):
+            out[j] = (np.uint64(h) << np.uint64(32)) | np.uint64(lb)
+    return out.view(np.float64)

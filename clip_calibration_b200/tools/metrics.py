@@ -68,7 +68,7 @@ def MCE(conf, pred, gt, conf_bin_num=10, group=None):
 def quantile_thresholds(keys: torch.Tensor, n_bins: int, quantile_method: str = "averaged_inverted_cdf",
                         group=None) -> np.ndarray:
     """Inner bin edges of KBinsDiscretizer(n_bins, strategy='quantile') fitted on `keys`
-    (float32, non-negative), from exact global order statistics computed on the device.
+    (float32 or float64, non-negative), from exact global order statistics computed on the device.
     Matches scikit-learn 1.9 for N <= 200,000; above that sklearn estimates the edges from an
     unseeded 200k subsample while this uses all N values."""
     n_local = keys.numel()
@@ -83,8 +83,9 @@ def quantile_thresholds(keys: torch.Tensor, n_bins: int, quantile_method: str = 
     look = dict(zip(ranks.tolist(), vals))
     if look[0] == look[n - 1]:
         return np.zeros(0, np.float64)          # constant column: sklearn collapses to one bin
-    x_lo = np.array([look[int(r)] for r in lo], np.float32)
-    x_hi = np.array([look[int(r)] for r in hi], np.float32)
+    dt = np.float64 if keys.dtype == torch.float64 else np.float32
+    x_lo = np.array([look[int(r)] for r in lo], dt)
+    x_hi = np.array([look[int(r)] for r in hi], dt)
     edges = tm.edges_from_order_stats(x_lo, x_hi, gamma)
     return edges[1:-1]
 
@@ -92,8 +93,9 @@ def quantile_thresholds(keys: torch.Tensor, n_bins: int, quantile_method: str = 
 def AdaptiveECE(conf, pred, gt, conf_bin_num=10, quantile_method="averaged_inverted_cdf", group=None):
     """Equal-mass-bin ECE, reference tools/metrics.py:212-236."""
     c = _conf_dev(conf)
-    keys = c if c.dtype == torch.float32 else c.to(torch.float32)
-    thr = quantile_thresholds(keys, conf_bin_num, quantile_method, group)
+    # float64 confidences (isotonic / density-ratio outputs) keep their own resolution: edges from float64 order
+    # statistics, binning of the float64 values - what KBinsDiscretizer does with a float64 column
+    thr = quantile_thresholds(c, conf_bin_num, quantile_method, group)
     table = native.bin_stats(c, _pred_dev(pred), _dev(gt, torch.int64), thr)
     return tm.sum_of_gaps(native.table_to_numpy(_allreduce(table, group)))
 

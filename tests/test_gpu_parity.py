@@ -65,6 +65,31 @@ def test_bin_stats_large_random_and_order_statistics(cuda_lib):
                - orc.adaptive_ece(small, pred[:150000], gt[:150000], 10)) < 1e-7
 
 
+def test_adaptive_ece_on_float64_plateaus(cuda_lib):
+    """Calibrated confidences are float64 (isotonic / density-ratio outputs: a plateau value + 1e-9 * p): thousands of
+    values that differ far below float32 resolution.  KBinsDiscretizer works on the float64 column - its edges fall
+    INSIDE plateaus - so the order statistics and the binning must be float64 too."""
+    rng = np.random.default_rng(17)
+    n = 60_000
+    plateau = rng.choice(np.array([0.12, 0.31, 0.48, 0.52, 0.77, 0.93]), size=n, p=[0.1, 0.15, 0.2, 0.25, 0.2, 0.1])
+    conf = plateau + 1e-9 * rng.random(n)
+    assert len(np.unique(conf.astype(np.float32))) <= 6 and len(np.unique(conf)) > n // 2
+    pred = rng.integers(0, 5, n)
+    gt = np.where(rng.random(n) < plateau, pred, (pred + 1) % 5)
+    ranks = [0, 7, n // 10, n // 3, n // 2, n - 2, n - 1]
+    got = native.order_statistics(torch.from_numpy(conf).cuda(), ranks)
+    assert got.dtype == np.float64 and np.array_equal(got, np.sort(conf)[ranks])
+    for nb in (10, 15):
+        want = orc.adaptive_ece(conf, pred, gt, nb)
+        assert abs(metrics.AdaptiveECE(conf, pred, gt, nb) - want) < 1e-9, nb
+        # rounding the column to float32 first is a different (coarser) binning - the deviation the fix removes
+    from clip_calibration_b200.evaluators import vl_evaluator
+    probs = np.full((n, 5), 0.0)
+    probs[np.arange(n), pred] = conf
+    res = vl_evaluator.evaluate(probs, gt)
+    assert abs(res["ace"] - 100.0 * orc.adaptive_ece(conf, pred, gt, 10)) < 1e-7
+
+
 def test_piece_matches_reference(cuda_lib, golden):
     g = golden("proximity_piece")
     prox = np.exp(-np.mean(g["knn"], axis=-1))
