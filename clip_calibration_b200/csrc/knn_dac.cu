@@ -312,6 +312,25 @@ __global__ void dac_map_kernel(const float* __restrict__ dist_zs, const float* _
   class_conf[i] = dac_map_value(a, b, k, kk);
 }
 
+__device__ __forceinline__ unsigned long long pack2f(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add2f(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2f(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // ---- small DAC fits in ONE launch -------------------------------------------------------------------------
 // EuroSAT / SUN397 / ImageNet-sized vocabularies (C x B up to ~2M pairs) are latency-bound: the general path is a
 // chain of ~19 launches (two kNN problems x {split, tensor-core filter, verify, redo, ...} + the map) of which each
@@ -320,6 +339,25 @@ __global__ void dac_map_kernel(const float* __restrict__ dist_zs, const float* _
 // differences, so the floats are those of ccal_knn_l2_exhaustive) and leaves a sorted partial list per query row;
 // the LAST CTA of a query tile (atomic ticket) merges the partial lists by (distance, index) and writes the
 // neighbours; the last of the two problems then applies the DAC map to the tile's 64 classes.
+// All lanes call.  Each lane holds n candidates (distance bits of non-negative floats, index; 0x7f800000 / 0x7fffffff
+// = none).  On return (pd, pi) is the smallest candidate of the whole warp that comes strictly after the incoming
+// (pd, pi) in (distance, index) order - calling it cap times walks the cap smallest in order.
+__device__ __forceinline__ void warp_next_smallest(const unsigned int* cd, const int* ci, int n, unsigned int& pd, int& pi) {
+  unsigned int bd = 0x7f800000u;
+  int bi = 0x7fffffff;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (u < n) {
+      const bool after = cd[u] > pd || (cd[u] == pd && ci[u] > pi);
+      if (after && (cd[u] < bd || (cd[u] == bd && ci[u] < bi))) { bd = cd[u]; bi = ci[u]; }
+    }
+  }
+  const unsigned int md = __reduce_min_sync(0xffffffffu, bd);
+  const int mi = __reduce_min_sync(0xffffffffu, bd == md ? bi : 0x7fffffff);
+  pd = md;
+  pi = mi;
+}
+
 struct DacSmallParams {
   const float* ref[2];
   const float* qry[2];
@@ -349,11 +387,12 @@ dac_fit_small_kernel(const __grid_constant__ DacSmallParams P) {
   const long long q0 = (long long)qt * kTile, r0 = (long long)rt * kTile;
   const long long ld_q = (q0 + ld_row < P.c) ? q0 + ld_row : -1;
 
-  float acc[4][4];
+  // squared distances accumulate as packed fp32 pairs (FADD2 / FFMA2: the same IEEE operations in the same order as
+  // the scalar tiled scan, two per instruction - sm_100 issues packed pairs at twice the lane rate of scalar FFMA);
+  // the query chunk is staged NEGATED so that r - q is one packed add
+  unsigned long long acc2[4][2];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int bb = 0; bb < 4; ++bb) acc[a][bb] = 0.f;
+  for (int a = 0; a < 4; ++a) { acc2[a][0] = 0ull; acc2[a][1] = 0ull; }
   float4 qv[kChunk / 16], rv[kChunk / 16];
   auto load_chunk = [&](int d0) {
 #pragma unroll
@@ -373,8 +412,8 @@ dac_fit_small_kernel(const __grid_constant__ DacSmallParams P) {
 #pragma unroll
     for (int h = 0; h < kChunk / 16; ++h) {
       const int c0 = 16 * h + ld_col;
-      Qs[c0 + 0][ld_row] = qv[h].x; Qs[c0 + 1][ld_row] = qv[h].y;
-      Qs[c0 + 2][ld_row] = qv[h].z; Qs[c0 + 3][ld_row] = qv[h].w;
+      Qs[c0 + 0][ld_row] = -qv[h].x; Qs[c0 + 1][ld_row] = -qv[h].y;
+      Qs[c0 + 2][ld_row] = -qv[h].z; Qs[c0 + 3][ld_row] = -qv[h].w;
       Rs[c0 + 0][ld_row] = rv[h].x; Rs[c0 + 1][ld_row] = rv[h].y;
       Rs[c0 + 2][ld_row] = rv[h].z; Rs[c0 + 3][ld_row] = rv[h].w;
     }
@@ -382,41 +421,57 @@ dac_fit_small_kernel(const __grid_constant__ DacSmallParams P) {
     if (d0 + kChunk < d) load_chunk(d0 + kChunk);
 #pragma unroll
     for (int kk = 0; kk < kChunk; ++kk) {
-      const float4 q4 = *reinterpret_cast<const float4*>(&Qs[kk][ty * 4]);
+      const float4 q4 = *reinterpret_cast<const float4*>(&Qs[kk][ty * 4]);          // -q
       const float4 r4 = *reinterpret_cast<const float4*>(&Rs[kk][tx * 4]);
-      const float qa[4] = {q4.x, q4.y, q4.z, q4.w};
-      const float ra[4] = {r4.x, r4.y, r4.z, r4.w};
+      const float nq[4] = {q4.x, q4.y, q4.z, q4.w};
+      const unsigned long long r01 = pack2f(r4.x, r4.y), r23 = pack2f(r4.z, r4.w);
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          const float df = ra[bb] - qa[a];
-          acc[a][bb] = fmaf(df, df, acc[a][bb]);
-        }
+      for (int a = 0; a < 4; ++a) {
+        const unsigned long long nqa = pack2f(nq[a], nq[a]);
+        const unsigned long long d01 = add2f(r01, nqa), d23 = add2f(r23, nqa);          // r + (-q) == r - q exactly
+        acc2[a][0] = fma2f(d01, d01, acc2[a][0]);
+        acc2[a][1] = fma2f(d23, d23, acc2[a][1]);
+      }
     }
   }
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int bb = 0; bb < 4; ++bb) Dt[ty * 4 + a][tx * 4 + bb] = sqrtf(acc[a][bb]);
+  for (int a = 0; a < 4; ++a) {
+    float v0, v1, v2, v3;
+    unpack2f(acc2[a][0], v0, v1);
+    unpack2f(acc2[a][1], v2, v3);
+    Dt[ty * 4 + a][tx * 4 + 0] = sqrtf(v0); Dt[ty * 4 + a][tx * 4 + 1] = sqrtf(v1);
+    Dt[ty * 4 + a][tx * 4 + 2] = sqrtf(v2); Dt[ty * 4 + a][tx * 4 + 3] = sqrtf(v3);
+  }
   __syncthreads();
 
-  // sorted partial list (by distance, then index) of every query row over this reference tile
+  // sorted partial list (by distance, then index) of every query row over this reference tile: `cap` rounds of a
+  // warp-wide arg-min over the lane-local candidates that come after the previous winner in (distance, index) order
+  // (two REDUX per round instead of a serial insertion per candidate)
 #pragma unroll 1
   for (int r = 0; r < kRowsPerWarp; ++r) {
     const int row = warp * kRowsPerWarp + r;
     const long long q = q0 + row;
-    TopList mine{CUDART_INF_F, 0x7fffffff};
+    unsigned int cd[2];
+    int ci[2];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int col = lane + 32 * half;
       const bool ok = r0 + col < P.b;
-      list_offer(mine, ok ? Dt[row][col] : CUDART_INF_F, ok ? (int)(r0 + col) : -1, cap, lane);
+      cd[half] = ok ? __float_as_uint(Dt[row][col]) : 0x7f800000u;       // non-negative floats order like their bits
+      ci[half] = ok ? (int)(r0 + col) : 0x7fffffff;
+    }
+    unsigned int pd = 0u;
+    int pi = -1;
+    unsigned int my_d = 0x7f800000u;
+    int my_i = 0x7fffffff;
+    for (int t = 0; t < cap; ++t) {
+      warp_next_smallest(cd, ci, 2, pd, pi);
+      if (lane == t) { my_d = pd; my_i = pi; }
     }
     if (q < P.c && lane < cap) {
       const long long o = (((long long)prob * P.c + q) * P.n_rt + rt) * cap + lane;
-      P.part_d[o] = mine.d;
-      P.part_i[o] = mine.i;
+      P.part_d[o] = __uint_as_float(my_d);
+      P.part_i[o] = my_i;
     }
   }
   __threadfence();
@@ -426,25 +481,52 @@ dac_fit_small_kernel(const __grid_constant__ DacSmallParams P) {
   if (!s_last) return;
   __threadfence();
 
-  // merge the partial lists of this query tile
+  // merge the partial lists of this query tile (same arg-min rounds over the n_rt * cap candidates, re-read from L2
+  // each round when a lane holds more than four of them)
   const int k = P.k;
 #pragma unroll 1
   for (int r = 0; r < kRowsPerWarp; ++r) {
     const long long q = q0 + warp * kRowsPerWarp + r;
     if (q >= P.c) continue;                              // warp-uniform
-    TopList all{CUDART_INF_F, 0x7fffffff};
     const int total = P.n_rt * cap;
     const long long o = ((long long)prob * P.c + q) * total;
-    for (int t0 = 0; t0 < total; t0 += 32) {
-      const int t = t0 + lane;
-      const float cd = t < total ? __ldcg(P.part_d + o + t) : CUDART_INF_F;
-      const int ci = t < total ? __ldcg(P.part_i + o + t) : -1;
-      list_offer(all, cd, ci == 0x7fffffff ? -1 : ci, cap, lane);
+    unsigned int pd = 0u;
+    int pi = -1;
+    unsigned int my_d = 0x7f800000u;
+    int my_i = -1;
+    if (total <= 128) {
+      unsigned int cd[4];
+      int ci[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = lane + 32 * u;
+        cd[u] = t < total ? __float_as_uint(__ldcg(P.part_d + o + t)) : 0x7f800000u;
+        ci[u] = t < total ? __ldcg(P.part_i + o + t) : 0x7fffffff;
+      }
+      for (int t = 0; t < cap; ++t) {
+        warp_next_smallest(cd, ci, 4, pd, pi);
+        if (lane == t) { my_d = pd; my_i = pi; }
+      }
+    } else {
+      for (int t = 0; t < cap; ++t) {
+        unsigned int bd = 0x7f800000u;
+        int bi = 0x7fffffff;
+        for (int u = lane; u < total; u += 32) {
+          const unsigned int d1 = __float_as_uint(__ldcg(P.part_d + o + u));
+          const int i1 = __ldcg(P.part_i + o + u);
+          const bool after = d1 > pd || (d1 == pd && i1 > pi);
+          if (after && (d1 < bd || (d1 == bd && i1 < bi))) { bd = d1; bi = i1; }
+        }
+        const unsigned int md = __reduce_min_sync(0xffffffffu, bd);
+        const int mi = __reduce_min_sync(0xffffffffu, bd == md ? bi : 0x7fffffff);
+        pd = md; pi = mi;
+        if (lane == t) { my_d = pd; my_i = pi; }
+      }
     }
     if (lane < k) {
-      const bool have = lane < cap;
-      P.dist[prob][q * k + lane] = have ? all.d : CUDART_INF_F;
-      if (P.idx[prob]) P.idx[prob][q * k + lane] = have ? all.i : -1;
+      const bool have = lane < cap && my_i != 0x7fffffff;
+      P.dist[prob][q * k + lane] = have ? __uint_as_float(my_d) : CUDART_INF_F;
+      if (P.idx[prob]) P.idx[prob][q * k + lane] = have ? my_i : -1;
     }
   }
   __threadfence();
