@@ -365,8 +365,23 @@ def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2
             return pipeline.dac_fit_sharded(base_zs, txt_zs, base_tuned, txt_tuned, w.k)
         return native.dac_fit(base_zs, txt_zs, base_tuned, txt_tuned, w.k)[0]
 
+    side = pipeline._side_stream(img.device)
+    held = {}
+
     def compute(record=False):
         """DAC fit + fused scoring/binning (per-image pred / conf are written too: 8 B/image)"""
+        if use_graph:
+            # launch-bound shapes: the fit (which pass 1 does not need) runs on a side stream underneath pass 1,
+            # pass 2 joins them - the two-launch form of the same scoring call, bit-identical to the fused one
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                held["cc"] = fit()
+            table.zero_()
+            dotmax, pred = native.score_pass1(img, txt_op)
+            main.wait_stream(side)
+            held["out"] = (pred, native.score_pass2(img, txt_op, dotmax, pred, held["cc"], LOGIT_SCALE, labels, thr, table))
+            return
         cc = fit()
         table.zero_()
         if record:
@@ -384,12 +399,12 @@ def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2
     graph = None
     if use_graph:
         # warm every lazy initialisation (function attributes, memory pools) before capturing
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+        warm = torch.cuda.Stream()
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm):
             for _ in range(3):
                 compute()
-        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.current_stream().wait_stream(warm)
         torch.cuda.synchronize()
         launches_before = native.launch_count()
         try:
@@ -412,13 +427,15 @@ def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2
             dist.all_reduce(table)
         host_table.copy_(table, non_blocking=True)
 
-    def timed(fn, n_steps):
+    def timed(fn, n_steps, finish=None):
         ctx.barrier()
         if not need_flush:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(n_steps):
                 fn()
+            if finish is not None:
+                finish()
             e1.record()
             ctx.barrier()
             total = e0.elapsed_time(e1)
@@ -429,6 +446,8 @@ def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 fn()
+                if finish is not None:
+                    finish()
                 e1.record()
                 pairs.append((e0, e1))
             ctx.barrier()
@@ -474,7 +493,9 @@ def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2
         e2e_table = {}
         chunk_rows = 262144 if n_images > 2 * 262144 else max(1024, -(-n_images // 4 // 128) * 128)
 
-        def e2e_step():
+        pending = []
+
+        def e2e_queue():
             # H2D of the four text matrices + DAC fit (class_confidence stays on the device); with several ranks the
             # text side is uploaded and fitted by rank 0 and broadcast over NVLink (the text features are replicated)
             scorer = pipeline.CalibratedScorer.from_dac(host_txt["bz"], host_txt["cz"], host_txt["bt"], host_txt["ct"],
@@ -482,17 +503,43 @@ def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2
                                                         operand_dtype=torch.bfloat16, share_text=world > 1,
                                                         overlap_fit=True)
             scorer.accumulate_host(host_img, host_labels, chunk_rows=chunk_rows)                 # chunked H2D + scoring
-            e2e_table["t"] = scorer.reduced_table()                                              # all-reduce + D2H
+            pending.append(scorer.reduced_table_async())                                         # all-reduce + D2H, queued
+
+        def e2e_drain(keep=0):
+            while len(pending) > keep:
+                e2e_table["t"] = pending.pop(0).result()                                         # host waits for the D2H
+                assert tm.total_count(e2e_table["t"]) == n_images * world
+
+        def e2e_step_blocking():
+            e2e_queue()
+            e2e_drain()
+
+        def e2e_step_pipelined():
+            # an evaluation LOOP (several test sets / shards in a row): step i's table is read on the host after step
+            # i+1 has been queued, so that step's uploads and first launches run underneath step i's last kernels.
+            # Every step's H2D copies, kernels, all-reduce and D2H read still lie inside the timed region (the last
+            # step is drained before the closing event).  Small (L2-flushed) shapes are timed one step at a time.
+            e2e_queue()
+            e2e_drain(keep=0 if need_flush else 1)
 
         for _ in range(2):
-            e2e_step()
+            e2e_step_blocking()
         e2e_steps = max(3, steps // 2)
-        e2e_ms = timed(e2e_step, e2e_steps)
-        assert tm.total_count(e2e_table["t"]) == n_images * world
+        blocking_ms = timed(e2e_step_blocking, e2e_steps)
+        for _ in range(3):            # two steps in flight need more device / pinned blocks: let the allocators reach
+            e2e_step_pipelined()      # their steady state (cudaMalloc / cudaHostAlloc synchronise the device)
+        e2e_drain()
+        e2e_ms = timed(e2e_step_pipelined, e2e_steps, finish=e2e_drain)
         h2d = host_img.numel() * 2 + host_labels.numel() * 8 + sum(v.numel() * v.element_size() for v in host_txt.values())
         res["e2e"] = {"value": n_images * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(3 * (N_BINS + 1) * 8),
-                      "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "chunk_rows": chunk_rows}
+                      "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "chunk_rows": chunk_rows,
+                      "mode": ("one step at a time (L2 flushed between steps)" if need_flush else
+                               "evaluation loop, software-pipelined by one step: the host reads step i's table after "
+                               "queueing step i+1; all copies of all steps are inside the timed region"),
+                      "blocking": {"value": n_images * world * e2e_steps / (blocking_ms * 1e-3),
+                                   "ms_per_step": blocking_ms / e2e_steps,
+                                   "mode": "each step's table is read back before the next step is queued"}}
         del host_img, host_labels
     return res
 

@@ -68,7 +68,7 @@ _STAGING = {}
 
 
 def _staging(device: torch.device, rows: int, d: int, dtype, tag: str = "ring") -> dict:
-    """Device staging buffers of accumulate_host, kept per (device, shape): two [rows, d] feature buffers + label
+    """Device staging buffers of accumulate_host, kept per (device, shape): three [rows, d] feature buffers + label
     buffers with their `copied` / `consumed` events.  Because they persist, a new call only has to wait for the
     previous user of the SAME buffer (its `consumed` event) instead of ordering its copies after everything on the
     compute stream."""
@@ -77,11 +77,12 @@ def _staging(device: torch.device, rows: int, d: int, dtype, tag: str = "ring") 
     if st is None:
         if len(_STAGING) > 8:                      # shapes changed: drop the old buffers
             _STAGING.clear()
-        n_buf = 2 if tag == "ring" else 1
+        n_buf = 3 if tag == "ring" else 1
         st = {"bufs": [torch.empty((rows, d), dtype=dtype, device=device) for _ in range(n_buf)],
               "lbufs": [torch.empty(rows, dtype=torch.int64, device=device) for _ in range(n_buf)],
               "copied": [torch.cuda.Event() for _ in range(n_buf)],
-              "consumed": [torch.cuda.Event() for _ in range(n_buf)]}
+              "consumed": [torch.cuda.Event() for _ in range(n_buf)],
+              "next": 0}                               # ring position, carried from call to call
         cur = torch.cuda.current_stream(device)
         for ev in st["consumed"]:
             ev.record(cur)                         # allocation (and any earlier use of that memory) precedes the first copy
@@ -97,6 +98,30 @@ def _copy_stream(device: torch.device) -> torch.cuda.Stream:
     if key not in _COPY_STREAMS:
         _COPY_STREAMS[key] = torch.cuda.Stream(device)
     return _COPY_STREAMS[key]
+
+
+class PendingTable:
+    """A reduced bin table on its way to the host (CalibratedScorer.reduced_table_async)."""
+
+    def __init__(self, host: torch.Tensor, done: torch.cuda.Event, keep_alive=None):
+        self._host, self._done, self._keep = host, done, keep_alive
+        self._out = None
+
+    def ready(self) -> bool:
+        return self._out is not None or self._done.query()
+
+    def result(self) -> np.ndarray:
+        if self._out is None:
+            self._done.synchronize()
+            out = self._host.numpy().view(np.uint64).copy()
+            self._host = self._keep = None
+            # the per-bin confidence sums are 64-bit fixed point (2^-40 units): 2^24 images of confidence ~1 fill them
+            if tm.total_count(out) > MAX_IMAGES_PER_TABLE:
+                raise OverflowError(f"{tm.total_count(out)} images in one bin table: the 2^-40 fixed-point confidence "
+                                    f"sums hold at most {MAX_IMAGES_PER_TABLE}; evaluate in shards of <= 2^24 images "
+                                    "(reset() between them) and add the float results")
+            self._out = out
+        return self._out
 
 
 class CalibratedScorer:
@@ -122,7 +147,7 @@ class CalibratedScorer:
         # evaluator mode: per-image (pred, conf, label) stay on the device (16 B/image) and per-class {tp, fp, fn}
         # are counted, so that evaluate() can report every key of the reference's evaluator (macro-F1, ACE, PIECE)
         self._fit_done = None                 # event of a DAC fit still running on a side stream (from_dac(overlap_fit=True))
-        self._text_uploaded = None            # ... and of its host->device uploads
+        self._device_was_busy = None          # from_dac(overlap_fit=True): was the compute stream busy when it was called?
         self.keep_outputs = bool(keep_outputs)
         self._kept = []                       # [(pred int32, conf float32, labels int64)] per scored shard
         self.class_counts = None
@@ -165,26 +190,50 @@ class CalibratedScorer:
             return torch.empty((rows, dim), dtype=kw["operand_dtype"], device=dev)
 
         if overlap_fit:
-            # scoring operand first, on the compute stream (and broadcast at once); everything the multipliers need
-            # goes to the side stream and is awaited by the first launch that uses them
-            cur_tuned_dev = _to_cuda_f32(cur_tuned, "current_text_features_tuned") if is_root else None
-            obj = cls(cur_tuned_dev if is_root else empty_text(), None, **kw)
+            # Host inputs go up on the COPY stream, scoring operand first: the copy stream is a FIFO shared with
+            # accumulate_host's image chunks, so a call queued while the previous evaluation is still being scored
+            # uploads its text side (and then its first image chunks) underneath that evaluation's last kernels
+            # instead of behind them.  The buffers are allocated under the copy stream (a block of the compute
+            # stream's pool could still be in use by kernels queued there) and handed to their readers by event.
+            dev = torch.device(kw["device"]) if kw.get("device") is not None else torch.device("cuda", torch.cuda.current_device())
+            comp = torch.cuda.current_stream(dev)
+            busy = not comp.query()          # earlier work (the previous evaluation) is still running on the device
+            side = _side_stream(dev)
+            copy = _copy_stream(dev)
+            names = ("current_text_features_tuned", "base_text_features_zs", "current_text_features_zs",
+                     "base_text_features_tuned")
+            staged, uploaded = [], False
+            if is_root:
+                for x, nm in zip((cur_tuned, base_zs, cur_zs, base_tuned), names):
+                    t = x.detach() if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+                    if t.dim() != 2:
+                        raise ValueError(f"{nm}: expected a [rows, D] matrix, got shape {tuple(t.shape)}")
+                    ev = None
+                    if not t.is_cuda:
+                        with torch.cuda.stream(copy):
+                            t = t.contiguous().to(device=dev, non_blocking=t.is_pinned())
+                            ev = torch.cuda.Event()
+                            ev.record(copy)
+                        uploaded = True
+                    staged.append((t, ev))
+                op_src, op_ev = staged[0]
+                if op_ev is not None:
+                    comp.wait_event(op_ev)
+                    op_src.record_stream(comp)
+            obj = cls(op_src if is_root else empty_text(), None, **kw)       # narrows / widens on the compute stream
             if shared:
                 torch.distributed.broadcast(obj.txt, src=src, group=group)
-            comp = torch.cuda.current_stream(obj.device)
-            side = _side_stream(obj.device)
-            side.wait_stream(comp)                                   # cur_tuned_dev is produced on the compute stream
+            if is_root and staged[0][1] is None:
+                side.wait_stream(comp)                               # device inputs were produced on the compute stream
             dac = DistanseAwareCalibration() if is_root else None
             with torch.cuda.stream(side):
                 if is_root:
-                    rest = [_to_cuda_f32(x, nm) for x, nm in ((base_zs, "base_text_features_zs"),
-                                                              (cur_zs, "current_text_features_zs"),
-                                                              (base_tuned, "base_text_features_tuned"))]
-                    # image copies queued later must not overtake these uploads on the copy engine
-                    # (accumulate_host orders its copy stream after this event once the first head chunk is on its way)
-                    obj._text_uploaded = torch.cuda.Event()
-                    obj._text_uploaded.record(side)
-                    dac.fit(rest[0], rest[1], rest[2], cur_tuned_dev, k, sync_host_copy=False)
+                    for t, ev in staged:
+                        if ev is not None:
+                            side.wait_event(ev)
+                            t.record_stream(side)
+                    f32 = [_to_cuda_f32(t, nm) for (t, _), nm in zip(staged, names)]
+                    dac.fit(f32[1], f32[2], f32[3], f32[0], k, sync_host_copy=False)
                     cc = dac.class_confidence_device
                 else:
                     cc = torch.empty(obj.txt.shape[0], dtype=torch.float32, device=obj.device)
@@ -192,11 +241,10 @@ class CalibratedScorer:
                     torch.distributed.broadcast(cc, src=src, group=group)
                 obj._fit_done = torch.cuda.Event()
                 obj._fit_done.record(side)
-            if cur_tuned_dev is not None:
-                cur_tuned_dev.record_stream(side)
             obj.class_conf = cc
             obj.class_conf.record_stream(comp)
             obj.dac = dac
+            obj._device_was_busy = busy
             return obj
 
         if not is_root:
@@ -241,9 +289,17 @@ class CalibratedScorer:
             labels = (labels if isinstance(labels, torch.Tensor) else torch.from_numpy(np.asarray(labels)))
             labels = labels.to(device=self.device, dtype=torch.int64)
         use_table = labels is not None and accumulate
-        self._await_fit()
-        pred, conf, _ = native.score_fused(img, self.txt, self.class_conf, self.logit_scale, labels,
-                                           self.thresholds if use_table else None, self.table if use_table else None)
+        if self._fit_done is not None and self.operand_dtype in (torch.float16, torch.bfloat16) and img.shape[0]:
+            # the DAC fit is still running on its side stream (from_dac(overlap_fit=True)): pass 1 needs no
+            # multipliers and runs underneath it; pass 2 waits for the fit.  Bit-identical to the fused launch.
+            dotmax, pred = native.score_pass1(img, self.txt)
+            self._await_fit()
+            conf = native.score_pass2(img, self.txt, dotmax, pred, self.class_conf, self.logit_scale, labels,
+                                      self.thresholds if use_table else None, self.table if use_table else None)
+        else:
+            self._await_fit()
+            pred, conf, _ = native.score_fused(img, self.txt, self.class_conf, self.logit_scale, labels,
+                                               self.thresholds if use_table else None, self.table if use_table else None)
         if use_table and self.keep_outputs:
             self._keep(pred, conf, labels)
         return pred, conf
@@ -289,13 +345,25 @@ class CalibratedScorer:
         n, d = image_features.shape
         labels = labels.to(torch.int64)
         comp = torch.cuda.current_stream(self.device)
+        # Latency mode or throughput mode?  If the device is idle, the first launch waits for the first bytes: small
+        # first chunks (ramp) and pass 1 underneath the DAC fit shorten that head.  If earlier work is still running
+        # (an evaluation loop that queues the next evaluation before reading the last result), the uploads and the
+        # fit are hidden underneath it anyway, and full-size chunks through the one-call scoring path are cheaper.
+        busy = self._device_was_busy if self._device_was_busy is not None else not comp.query()
+        self._device_was_busy = None
         if self._copy_stream is None:
             self._copy_stream = _copy_stream(self.device)
         copy = self._copy_stream
         chunk_rows = max(128, min(int(chunk_rows), n))
+        # the scoring kernels are persistent over 256-row tiles, one CTA pair per two SMs: a chunk that is a whole number
+        # of waves leaves no SM idle in the last wave of each of its launches
+        wave = 256 * max(1, torch.cuda.get_device_properties(self.device).multi_processor_count // 2)
+        if n > chunk_rows >= 4 * wave:
+            per = -(-n // -(-n // chunk_rows))                       # balanced: ceil(n / number of chunks)
+            chunk_rows = -(-per // wave) * wave
         bounds, lo = [], 0
         sizes = []
-        if ramp and n > chunk_rows:
+        if ramp and n > chunk_rows and not busy:
             step = min(16384, chunk_rows // 2)
             while step < chunk_rows and sum(sizes) + step < n - chunk_rows // 2:
                 sizes.append(step)
@@ -308,7 +376,7 @@ class CalibratedScorer:
         preds, confs = [], []
         stage = _staging(self.device, chunk_rows, d, self.operand_dtype)
         bufs, lbufs, copied, consumed = stage["bufs"], stage["lbufs"], stage["copied"], stage["consumed"]
-        if self._fit_done is not None and len(bounds) > 3 and self.operand_dtype in (torch.float16, torch.bfloat16):
+        if self._fit_done is not None and not busy and len(bounds) > 3 and self.operand_dtype in (torch.float16, torch.bfloat16):
             # The DAC fit is still running on its side stream (from_dac(overlap_fit=True)).  Pass 1 needs no
             # multipliers: run it on the head chunks as they arrive, underneath the fit and its uploads, then wait
             # for the fit and finish the head with ONE pass-2 launch.  Same results as the fused launch, bit for bit.
@@ -326,9 +394,6 @@ class CalibratedScorer:
                     hbuf[lo:hi].copy_(image_features[lo:hi], non_blocking=True)
                     hlab[lo:hi].copy_(labels[lo:hi], non_blocking=True)
                     arrived.record(copy)
-                    if j == 0 and self._text_uploaded is not None:
-                        copy.wait_event(self._text_uploaded)         # the fit's inputs go next on the link
-                        self._text_uploaded = None
                 comp.wait_event(arrived)
                 parts.append(native.score_pass1(hbuf[lo:hi], self.txt))
             dotmax = torch.cat([q[0] for q in parts])
@@ -343,8 +408,11 @@ class CalibratedScorer:
                 preds.append(pred)
                 confs.append(conf)
         self._await_fit()
-        for i, (lo, hi) in enumerate(bounds):
-            b = i & 1
+        for lo, hi in bounds:
+            # the ring position persists across calls: the first chunk of a call queued behind another evaluation goes
+            # to the buffer that frees up first, not to the one that evaluation's last chunk is still being scored from
+            b = stage["next"]
+            stage["next"] = (b + 1) % len(bufs)
             with torch.cuda.stream(copy):
                 copy.wait_event(consumed[b])                         # (recorded at creation / by the previous user)
                 bufs[b][: hi - lo].copy_(image_features[lo:hi], non_blocking=True)
@@ -365,22 +433,26 @@ class CalibratedScorer:
         return None
 
     # ------------------------------------------------------------------ results
-    def reduced_table(self) -> np.ndarray:
-        """The bin table summed over all ranks of `group` (one NCCL all-reduce of
-        3*(n_bins+1) int64 on the compute stream), as a host uint64 array."""
+    def reduced_table_async(self) -> "PendingTable":
+        """Queue the reduction of the bin table (one NCCL all-reduce of 3*(n_bins+1) int64 on the compute stream) and
+        its device->host copy into pinned memory, and return at once: `.result()` waits for exactly that copy.  An
+        evaluation loop over several shards / datasets calls this, queues the NEXT evaluation, and only then reads the
+        result - the next evaluation's uploads and first launches then run underneath this one's last kernels."""
         self.flush()
         t = self.table
         if self.group is not False and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size(self.group) > 1:
             t = t.clone()
             torch.distributed.all_reduce(t, group=self.group)
-        out = native.table_to_numpy(t)
-        # the per-bin confidence sums are 64-bit fixed point (2^-40 units): 2^24 images of confidence ~1 fill them
-        if tm.total_count(out) > MAX_IMAGES_PER_TABLE:
-            raise OverflowError(f"{tm.total_count(out)} images in one bin table: the 2^-40 fixed-point confidence sums "
-                                f"hold at most {MAX_IMAGES_PER_TABLE}; evaluate in shards of <= 2^24 images "
-                                "(reset() between them) and add the float results")
-        return out
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        return PendingTable(host, done, t)
+
+    def reduced_table(self) -> np.ndarray:
+        """The bin table summed over all ranks of `group`, as a host uint64 array (blocking)."""
+        return self.reduced_table_async().result()
 
     def _reduce_group(self):
         """The process group the tables are reduced over, or None when there is nothing to reduce."""

@@ -943,3 +943,29 @@ def test_two_launch_scoring_is_bit_identical(cuda_lib, golden):
     np.testing.assert_allclose(cc_now, golden("sun397_l14")["cc_k5"], rtol=3e-6)
     p3, c3 = scorer.score(img, labels)
     assert torch.equal(p3.cpu(), outs[0][0]) and torch.equal(c3.cpu(), outs[0][1])
+
+
+def test_pipelined_evaluation_loop_equals_blocking_steps(cuda_lib):
+    """An evaluation loop that queues step i+1 (text uploads on the copy stream, DAC fit on the side stream, chunked
+    image uploads) before reading step i's table (reduced_table_async) returns, for every step, exactly the table of
+    the blocking one-step-at-a-time form - staging buffers, the copy-stream FIFO and the allocator's stream pools
+    must keep the overlapped steps apart."""
+    cases = [synth.make_case(f"loop{i}", 6000 + 700 * i, 600, 300, 512, 5, 0.3, seed=10 + i) for i in range(3)]
+    pin = lambda a, dt=None: (torch.from_numpy(a) if dt is None else torch.from_numpy(a).to(dt)).pin_memory()
+    host = [dict(bz=pin(c.base_zs, torch.bfloat16), cz=pin(c.txt_zs, torch.bfloat16), bt=pin(c.base_tuned, torch.bfloat16),
+                 ct=pin(c.txt_tuned, torch.bfloat16), img=pin(c.img, torch.bfloat16), lab=pin(c.labels)) for c in cases]
+
+    def queue(h, overlap=True):
+        scorer = pipeline.CalibratedScorer.from_dac(h["bz"], h["cz"], h["bt"], h["ct"], k=5, logit_scale=100.0,
+                                                    operand_dtype=torch.bfloat16, group=False, overlap_fit=overlap)
+        scorer.accumulate_host(h["img"], h["lab"], chunk_rows=1024)
+        return scorer.reduced_table_async()
+
+    blocking = [queue(h, overlap=False).result() for h in host]
+    for _ in range(2):                                   # twice: the second round reuses every staging buffer
+        order = [0, 1, 2, 1, 0, 2]
+        pend = [queue(host[i]) for i in order]           # all six steps queued before any result is read
+        for i, p in zip(order, pend):
+            assert np.array_equal(p.result(), blocking[i])
+            assert p.ready() and p.result() is p.result()
+    assert tm.total_count(blocking[0]) == 6000
