@@ -201,7 +201,7 @@ knn_redo_scan_kernel(const float* __restrict__ ref, const float* __restrict__ qu
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int count = min(*qcount, kRedoSmallMax);
   const long long stride = (long long)gridDim.x * kRedoThreads;
-  for (int e = 0; e < count; ++e) {
+  for (int e = blockIdx.y; e < count; e += gridDim.y) {        // listed rows in parallel over grid.y (usually 0-4 rows)
     const long long q = qlist[e];
     for (int j = threadIdx.x; j < d; j += kRedoThreads) s_q[j] = query[q * d + j];
     __syncthreads();
@@ -705,8 +705,8 @@ int launch_knn_exact(const float* ref, const float* query, int64_t nr, int64_t n
     CCAL_CUDA_OK(ws.alloc(cells * (sizeof(float) + sizeof(int)), stream));
     float* part_d = reinterpret_cast<float*>(ws.ptr);
     int* part_i = reinterpret_cast<int*>(ws.ptr + cells * sizeof(float));
-    knn_redo_scan_kernel<<<parts, kRedoThreads, (size_t)d * sizeof(float), stream>>>(ref, query, (long long)nr, d, cap, qlist,
-                                                                                   qcount, part_d, part_i);
+    knn_redo_scan_kernel<<<dim3((unsigned)parts, 16), kRedoThreads, (size_t)d * sizeof(float), stream>>>(
+        ref, query, (long long)nr, d, cap, qlist, qcount, part_d, part_i);
     note_launch();
     knn_redo_merge_kernel<<<kRedoSmallMax, 32, 0, stream>>>(part_d, part_i, parts, cap, k, drop_first, dist_out, idx_out,
                                                             qlist, qcount);

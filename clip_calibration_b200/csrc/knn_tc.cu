@@ -21,6 +21,7 @@
 #include "sm100_ptx.cuh"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -32,6 +33,7 @@ constexpr int kTcRBytes = kTcBlockN * kTcBlockK * 2;     // 32 KB
 constexpr int kTcStages = 3;                              // barrier slots (pairs use 3 stages, single CTAs 2)
 constexpr int kTcThreads = 192;
 constexpr int kTcCtlBytes = 1024;
+constexpr int kTcScratchBytes = 32 * 128 * 4;            // epilogue staging: 32 scores of each of the 128 epilogue threads
 
 struct __align__(16) KnnCtl {
   uint64_t full[kTcStages];
@@ -42,47 +44,103 @@ struct __align__(16) KnnCtl {
 };
 
 // ---------------------------------------------------------------------------------------- 1
-// Output rows are d + 64 wide: the extra 64-feature block holds ONE non-zero column that folds the -|r|^2/2
-// term of the score into the GEMM itself: queries get 1.0 there, reference rows get -|r|^2/2 (as a hi/lo pair),
-// so the accumulator is directly  q.r - |r|^2/2  and the filter's epilogue is a bare compare per element.
+// Operand modes.  Features that are exactly representable in a 16-bit format - the reference's default precision is
+// fp16 (train.py:152), so its cached text / image features are; so are bf16 checkpoints - need no hi/lo split: one
+// MMA per K step gives exact products.  exact16_scan_kernel decides once per call, on the device:
+//   mode 1: every element of both matrices is a bf16 value   -> operands = bf16(x), one MMA
+//   mode 2: every element is an fp16 value                    -> operands = fp16(x), one MMA (kind::f16, fp16 inputs)
+//   mode 0: anything else -> x = hi + lo in bf16, three MMAs (hi.hi + hi.lo + lo.hi)
+// flags[0] != 0: some element is not a bf16 value; flags[1] != 0: some element is not an fp16 value of magnitude <= 4.
+__device__ __forceinline__ int operand_mode(const unsigned int* __restrict__ flags) {
+  return flags[0] == 0u ? 1 : (flags[1] == 0u ? 2 : 0);
+}
+
 __global__ void __launch_bounds__(256)
-split_rows_kernel(const float* __restrict__ x, long long rows, int d, __nv_bfloat16* __restrict__ hi,
-                  __nv_bfloat16* __restrict__ lo, float* __restrict__ half_norm2, unsigned int* __restrict__ max_norm2_bits,
-                  int is_reference) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + warp;
-  if (row >= rows) return;
+exact16_scan_kernel(const float* __restrict__ x, long long n_elems, unsigned int* __restrict__ flags) {
+  unsigned int not_bf16 = 0u, not_f16 = 0u;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems / 4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      not_bf16 |= (__bfloat162float(__float2bfloat16_rn(f[u])) != f[u]) ? 1u : 0u;
+      // fp16 mode also needs the folded -|r|^2/2 (<= d * max|x|^2 / 2) far inside fp16's range: |x| <= 4, d <= 1024
+      not_f16 |= (__half2float(__float2half_rn(f[u])) != f[u] || !(fabsf(f[u]) <= 4.0f)) ? 1u : 0u;
+    }
+  }
+  not_bf16 = __any_sync(0xffffffffu, not_bf16 != 0u);
+  not_f16 = __any_sync(0xffffffffu, not_f16 != 0u);
+  if ((threadIdx.x & 31) == 0) {
+    if (not_bf16) atomicOr(flags, 1u);
+    if (not_f16) atomicOr(flags + 1, 1u);
+  }
+}
+
+// Output rows are d + 64 wide: the extra 64-feature block folds the -|r|^2/2 term of the score into the GEMM itself.
+// Queries carry 1.0 in its first three columns, reference rows a three-term 16-bit expansion of -|r|^2/2 (each term
+// takes the next 8 or 11 mantissa bits, so the sum is the fp32 value exactly); the accumulator is then directly
+// q.r - |r|^2/2 and the filter's epilogue is a bare compare per element.  In mode 0 the lo matrix's extra block is zero.
+template <typename T16> __device__ __forceinline__ T16 to16(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 to16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half to16<__half>(float v) { return __float2half_rn(v); }
+template <typename T16> __device__ __forceinline__ float from16(T16 v);
+template <> __device__ __forceinline__ float from16<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float from16<__half>(__half v) { return __half2float(v); }
+
+template <typename T16, bool kWithLo>
+__device__ __forceinline__ void split_row(const float* __restrict__ x, long long row, int d, T16* __restrict__ hi,
+                                          T16* __restrict__ lo, float* __restrict__ half_norm2,
+                                          unsigned int* __restrict__ max_norm2_bits, int is_reference, int lane) {
   const int dp = d + kTcBlockK;
   const float4* src = reinterpret_cast<const float4*>(x + row * d);
   float acc = 0.f;
   for (int j = lane; j < d / 4; j += 32) {
     const float4 v = src[j];
     const float f[4] = {v.x, v.y, v.z, v.w};
-    __nv_bfloat16 h[4], l[4];
+    T16 h[4], l[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      h[u] = __float2bfloat16_rn(f[u]);
-      l[u] = __float2bfloat16_rn(f[u] - __bfloat162float(h[u]));
+      h[u] = to16<T16>(f[u]);
+      l[u] = to16<T16>(f[u] - from16<T16>(h[u]));
       acc = fmaf(f[u], f[u], acc);
     }
     *reinterpret_cast<uint2*>(hi + row * dp + 4 * j) = *reinterpret_cast<uint2*>(h);
-    *reinterpret_cast<uint2*>(lo + row * dp + 4 * j) = *reinterpret_cast<uint2*>(l);
+    if (kWithLo) *reinterpret_cast<uint2*>(lo + row * dp + 4 * j) = *reinterpret_cast<uint2*>(l);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  // extra block: column d carries the fold term, columns d+1 .. d+63 are zero
-  const float extra = is_reference ? -0.5f * acc : 1.0f;
-  const __nv_bfloat16 eh = __float2bfloat16_rn(extra);
-  const __nv_bfloat16 el = __float2bfloat16_rn(extra - __bfloat162float(eh));
-  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  // extra block: columns d .. d+2 carry the fold term, the rest is zero
+  float e[3];
+  if (is_reference) {
+    float rest = -0.5f * acc;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) { e[u] = from16<T16>(to16<T16>(rest)); rest -= e[u]; }
+  } else {
+    e[0] = e[1] = e[2] = 1.0f;
+  }
   for (int j = lane; j < kTcBlockK; j += 32) {
-    hi[row * dp + d + j] = (j == 0) ? eh : zero;
-    lo[row * dp + d + j] = (j == 0) ? el : zero;
+    hi[row * dp + d + j] = to16<T16>(j < 3 ? e[j] : 0.f);
+    if (kWithLo) lo[row * dp + d + j] = to16<T16>(0.f);
   }
   if (lane == 0) {
     half_norm2[row] = 0.5f * acc;
     if (max_norm2_bits) atomicMax(max_norm2_bits, __float_as_uint(acc));   // non-negative floats order like uints
   }
+}
+
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ x, long long rows, int d, __nv_bfloat16* __restrict__ hi,
+                  __nv_bfloat16* __restrict__ lo, float* __restrict__ half_norm2, unsigned int* __restrict__ max_norm2_bits,
+                  int is_reference, const unsigned int* __restrict__ flags) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const int mode = operand_mode(flags);                 // uniform over the grid
+  if (mode == 0) split_row<__nv_bfloat16, true>(x, row, d, hi, lo, half_norm2, max_norm2_bits, is_reference, lane);
+  else if (mode == 1) split_row<__nv_bfloat16, false>(x, row, d, hi, lo, half_norm2, max_norm2_bits, is_reference, lane);
+  else split_row<__half, false>(x, row, d, reinterpret_cast<__half*>(hi), reinterpret_cast<__half*>(lo), half_norm2,
+                                max_norm2_bits, is_reference, lane);
 }
 
 // ---------------------------------------------------------------------------------------- 2
@@ -91,9 +149,18 @@ struct KnnTcParams {
   int kblocks, n_col_tiles, n_row_tiles;
   uint32_t idesc;
   const float* r_half_norm2;     // [nr]
-  int* cand_idx;                 // [nq, KP]
-  float* cand_cut;               // [nq] score of the worst kept candidate (-inf if the list is not full)
+  const unsigned int* flags;     // operand mode (exact16_scan_kernel)
+  int n_slots;                   // candidate lists per query: one per work unit that touches the query's row tile
+  int* cand_idx;                 // [nq, n_slots, KP]  (-1 = empty; zero-filled slots are never written)
+  float* cand_score;             // [nq, n_slots, KP]  GEMM score q.r - |r|^2/2 of each candidate, descending per slot
 };
+
+// Work decomposition (stream-K style): the (row tile, reference tile) pairs are numbered t = tile * NT + nt and cut
+// into n_units equal contiguous ranges, one per CTA (pair) - every SM gets the same number of 256 x 256 x D tiles
+// whatever the shape (86 row tiles on 74 pairs used to leave the second wave 16 % full).  A range may end inside
+// a row tile; each unit that touches a row tile leaves its own candidate list for those queries (slot = unit - first
+// unit touching the tile) and knn_verify_kernel merges the slots by score.
+__device__ __forceinline__ long long unit_begin(long long u, long long total, long long n_units) { return u * total / n_units; }
 
 // kCtas = 2: CTA pairs (cta_group::2): each CTA owns 128 query rows and loads only half (128 rows) of every
 // reference tile; stage = {Qhi, Qlo, Rhi/2, Rlo/2} = 64 KB, 3 stages.  kCtas = 1: 96 KB stages, 2 stages.
@@ -133,29 +200,34 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
   const int NT = p.n_col_tiles, KB = p.kblocks;
+  const long long total = (long long)p.n_row_tiles * NT;
+  const long long t_lo = unit_begin(unit, total, n_units), t_hi = unit_begin(unit + 1, total, n_units);
+  const int mode = operand_mode(p.flags);
+  const bool single = mode != 0;                 // 16-bit-exact operands: hi tiles only, one MMA per K step
 
   if (warp == 0) {
     // TMA producer: whole warp loops, one elected lane issues (warp-uniform control flow)
     uint32_t stage = 0, phase = 0;
-    for (int tile = unit; tile < p.n_row_tiles; tile += n_units) {
-      const int row0 = tile * kTileRows + (int)rank * kTcBlockM;
-      for (int nt = 0; nt < NT; ++nt) {
+    for (long long t = t_lo; t < t_hi; ++t) {
+      {
+        const int tile = (int)(t / NT), nt = (int)(t % NT);
+        const int row0 = tile * kTileRows + (int)rank * kTcBlockM;
         const int col0 = nt * kTcBlockN + (int)rank * kRRows;
         for (int kb = 0; kb < KB; ++kb) {
           unsigned char* sp = op_ptr + (size_t)stage * kStageBytes;
           ptx::mbar_wait(&ctl->empty[stage], phase ^ 1u);
           if (ptx::elect_one()) {
-            if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[stage], kStageBytes * kCtas);
+            if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[stage], (single ? kStageBytes / 2 : kStageBytes) * kCtas);
             if (kCtas == 2) {
               ptx::tma_load_2d_2sm(sp, &map_qhi, &ctl->full[stage], kb * kTcBlockK, row0, ptx::kEvictNormal);
-              ptx::tma_load_2d_2sm(sp + kTcQBytes, &map_qlo, &ctl->full[stage], kb * kTcBlockK, row0, ptx::kEvictNormal);
+              if (!single) ptx::tma_load_2d_2sm(sp + kTcQBytes, &map_qlo, &ctl->full[stage], kb * kTcBlockK, row0, ptx::kEvictNormal);
               ptx::tma_load_2d_2sm(sp + 2 * kTcQBytes, &map_rhi, &ctl->full[stage], kb * kTcBlockK, col0, ptx::kEvictLast);
-              ptx::tma_load_2d_2sm(sp + 2 * kTcQBytes + kRBytes, &map_rlo, &ctl->full[stage], kb * kTcBlockK, col0, ptx::kEvictLast);
+              if (!single) ptx::tma_load_2d_2sm(sp + 2 * kTcQBytes + kRBytes, &map_rlo, &ctl->full[stage], kb * kTcBlockK, col0, ptx::kEvictLast);
             } else {
               ptx::tma_load_2d(sp, &map_qhi, &ctl->full[stage], kb * kTcBlockK, row0, ptx::kEvictNormal);
-              ptx::tma_load_2d(sp + kTcQBytes, &map_qlo, &ctl->full[stage], kb * kTcBlockK, row0, ptx::kEvictNormal);
+              if (!single) ptx::tma_load_2d(sp + kTcQBytes, &map_qlo, &ctl->full[stage], kb * kTcBlockK, row0, ptx::kEvictNormal);
               ptx::tma_load_2d(sp + 2 * kTcQBytes, &map_rhi, &ctl->full[stage], kb * kTcBlockK, col0, ptx::kEvictLast);
-              ptx::tma_load_2d(sp + 2 * kTcQBytes + kRBytes, &map_rlo, &ctl->full[stage], kb * kTcBlockK, col0, ptx::kEvictLast);
+              if (!single) ptx::tma_load_2d(sp + 2 * kTcQBytes + kRBytes, &map_rlo, &ctl->full[stage], kb * kTcBlockK, col0, ptx::kEvictLast);
             }
           }
           __syncwarp();
@@ -167,8 +239,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
     // MMA issuer (pair leader): whole warp waits, one elected lane issues 12 MMAs + commit per 64-feature block
     if (leader) {
       uint32_t stage = 0, phase = 0, acc_it = 0;
-      for (int tile = unit; tile < p.n_row_tiles; tile += n_units)
-        for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+      // instruction descriptor: A / B format bits 7-9 / 10-12 (1 = bf16, 0 = fp16) follow the operand mode
+      const uint32_t fmt = (mode == 2) ? 0u : 1u;
+      const uint32_t idesc = p.idesc | (fmt << 7) | (fmt << 10);
+      for (long long t = t_lo; t < t_hi; ++t, ++acc_it) {
+        {
           const uint32_t as = acc_it & 1u, aph = (acc_it >> 1) & 1u;
           ptx::mbar_wait(&ctl->tmem_empty[as], aph ^ 1u);
           ptx::tc_fence_after();
@@ -182,14 +257,22 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
               const uint64_t rhi = ptx::make_kmajor_sw128_desc(sp + 2 * kTcQBytes);
               const uint64_t rlo = ptx::make_kmajor_sw128_desc(sp + 2 * kTcQBytes + kRBytes);
               auto mma = [&](uint64_t ad, uint64_t bd, uint32_t acc) {
-                if (kCtas == 2) ptx::umma_f16_2sm(d_tmem, ad, bd, p.idesc, acc); else ptx::umma_f16(d_tmem, ad, bd, p.idesc, acc);
+                if (kCtas == 2) ptx::umma_f16_2sm(d_tmem, ad, bd, idesc, acc); else ptx::umma_f16(d_tmem, ad, bd, idesc, acc);
               };
+              if (single) {
 #pragma unroll
-              for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k) {
-                const uint64_t o = (uint64_t)(k * 2);
-                mma(qhi + o, rhi + o, (uint32_t)((kb | k) != 0));
-                mma(qhi + o, rlo + o, 1u);
-                mma(qlo + o, rhi + o, 1u);
+                for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k) {
+                  const uint64_t o = (uint64_t)(k * 2);
+                  mma(qhi + o, rhi + o, (uint32_t)((kb | k) != 0));
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < kTcBlockK / kTcUmmaK; ++k) {
+                  const uint64_t o = (uint64_t)(k * 2);
+                  mma(qhi + o, rhi + o, (uint32_t)((kb | k) != 0));
+                  mma(qhi + o, rlo + o, 1u);
+                  mma(qlo + o, rhi + o, 1u);
+                }
               }
               if (kCtas == 2) ptx::umma_commit_2sm(&ctl->empty[stage]); else ptx::umma_commit(&ctl->empty[stage]);
               if (kb == KB - 1) {
@@ -200,18 +283,25 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
+      }
     }
   } else {
     const int quarter = warp & 3;
     const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+    float* sc = reinterpret_cast<float*>(op_ptr + (size_t)kStages * kStageBytes);   // [32 columns][128 epilogue threads]
+    const int et = quarter * 32 + lane;
     uint32_t acc_it = 0;
-    for (int tile = unit; tile < p.n_row_tiles; tile += n_units) {
+    for (long long t = t_lo; t < t_hi;) {
+      // one segment = this unit's part [nt0, nt1) of one row tile
+      const int tile = (int)(t / NT), nt0 = (int)(t % NT);
+      const int nt1 = (int)min((long long)NT, (long long)nt0 + (t_hi - t));
+      t += nt1 - nt0;
       const long long row = (long long)tile * kTileRows + (long long)rank * kTcBlockM + quarter * 32 + lane;
       float ts[KP];
       int ti[KP];
 #pragma unroll
       for (int s = 0; s < KP; ++s) { ts[s] = -CUDART_INF_F; ti[s] = -1; }
-      for (int nt = 0; nt < NT; ++nt, ++acc_it) {
+      for (int nt = nt0; nt < nt1; ++nt, ++acc_it) {
         const uint32_t as = acc_it & 1u;
         ptx::mbar_wait(&ctl->tmem_full[as], (acc_it >> 1) & 1u);
         ptx::tc_fence_after();
@@ -229,10 +319,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
           for (int j = 0; j < 32; ++j) hits |= (uint32_t)(__uint_as_float(raw[j]) > worst) << j;
           if (nv < 32) hits &= (1u << nv) - 1u;
           if (hits) {                                              // rare once the lists have warmed up
+            // Stage this lane's 32 scores in shared memory and walk only ITS OWN hit bits (dynamic index): a warp
+            // whose lanes hit at different columns used to step through all 32 columns with the insertion predicated
+            // per lane - with few reference rows (lists never warm) that loop, not the GEMM, set the kernel's time.
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float t = __uint_as_float(raw[j]);
-              if (((hits >> j) & 1u) && t > ts[KP - 1]) {
+            for (int j = 0; j < 32; ++j) sc[j * 128 + et] = __uint_as_float(raw[j]);
+            while (hits) {
+              const int j = __ffs(hits) - 1;
+              hits &= hits - 1u;
+              const float t = sc[j * 128 + et];
+              if (t > ts[KP - 1]) {
                 // sorted insert, descending; equal scores keep the earlier (lower) index ahead
                 float ct = t;
                 int ci = col0 + j;
@@ -257,9 +353,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
         }
       }
       if (row < p.nq) {
+        // first unit whose range reaches this row tile: the largest u with unit_begin(u) <= tile * NT
+        const long long first = (((long long)tile * NT + 1) * n_units - 1) / total;
+        const long long o = (row * p.n_slots + (unit - first)) * KP;
 #pragma unroll
-        for (int s = 0; s < KP; ++s) p.cand_idx[row * KP + s] = ti[s];
-        p.cand_cut[row] = (ti[KP - 1] >= 0) ? ts[KP - 1] : -CUDART_INF_F;
+        for (int s = 0; s < KP; ++s) { p.cand_idx[o + s] = ti[s]; p.cand_score[o + s] = ts[s]; }
       }
     }
   }
@@ -274,18 +372,77 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant
 
 // ---------------------------------------------------------------------------------------- 3
 // One warp per query.  eps bounds the error of the GEMM-derived d^2.
+constexpr int kMaxSlots = 4;                     // candidate lists per query (work units touching one row tile)
+
 template <int KP>
 __global__ void __launch_bounds__(256)
 knn_verify_kernel(const float* __restrict__ ref, const float* __restrict__ query, long long nr, long long nq, int d,
-                  int k, int drop_first, const int* __restrict__ cand_idx, const float* __restrict__ cand_cut,
+                  int k, int drop_first, int n_slots, const int* __restrict__ cand_idx, const float* __restrict__ cand_score,
                   const float* __restrict__ q_half_norm2, const unsigned int* __restrict__ r_max_norm2_bits,
                   float* __restrict__ dist_out, int* __restrict__ idx_out, int* __restrict__ redo_list,
                   int* __restrict__ redo_count) {
+  __shared__ int s_idx[8][KP];
+  __shared__ float s_score[8][KP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long q = (long long)blockIdx.x * 8 + warp;
   if (q >= nq) return;
   const float4* qv = reinterpret_cast<const float4*>(query + q * d);
-  const int my_idx = lane < KP ? cand_idx[q * KP + lane] : -1;
+  // Merge the slots: the KP best GEMM scores over all of them, ties to the lower index.  Every row a unit discarded
+  // scores at most that unit's KP-th entry, which is at most the merged KP-th score - the cut of the proof below.
+  constexpr int kPerLane = (kMaxSlots * KP + 31) / 32;
+  const int m_total = n_slots * KP;
+  float es[kPerLane];
+  int ei[kPerLane];
+#pragma unroll
+  for (int u = 0; u < kPerLane; ++u) {
+    const int e = lane + 32 * u;
+    ei[u] = e < m_total ? cand_idx[q * m_total + e] : -1;
+    es[u] = (e < m_total && ei[u] >= 0) ? cand_score[q * m_total + e] : -CUDART_INF_F;
+  }
+  if (lane < KP) { s_idx[warp][lane] = -1; s_score[warp][lane] = -CUDART_INF_F; }
+  __syncwarp();
+  int rk[kPerLane];
+#pragma unroll
+  for (int u = 0; u < kPerLane; ++u) rk[u] = 0;
+#pragma unroll
+  for (int u2 = 0; u2 < kPerLane; ++u2) {
+    if (u2 * 32 < m_total) {                                   // warp-uniform
+      for (int l = 0; l < 32; ++l) {
+        const float os = __shfl_sync(0xffffffffu, es[u2], l);
+        const int oi = __shfl_sync(0xffffffffu, ei[u2], l);
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u)
+          rk[u] += (oi >= 0 && (os > es[u] || (os == es[u] && oi < ei[u]))) ? 1 : 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kPerLane; ++u)
+    if (ei[u] >= 0 && rk[u] < KP) { s_idx[warp][rk[u]] = ei[u]; s_score[warp][rk[u]] = es[u]; }
+  __syncwarp();
+  int my_idx = lane < KP ? s_idx[warp][lane] : -1;
+  float cut = (s_idx[warp][KP - 1] >= 0) ? s_score[warp][KP - 1] : -CUDART_INF_F;
+  const int want = k + (drop_first ? 1 : 0);                // list length the caller needs
+  const int have = (int)min((long long)want, nr);
+  const float qn2 = 2.0f * q_half_norm2[q];
+  // |S_gemm - S| <= ~1.2e-5 |q||r| (dropped lo.lo + bf16 rounding of lo + fp32 accumulation);
+  // d^2 carries twice that; |q||r| <= (|q|^2 + max|r|^2)/2; 4x safety factor
+  const float eps = 5e-5f * (qn2 + __uint_as_float(*r_max_norm2_bits));
+  // Candidates ranked beyond `want` whose GEMM score lies more than 4 eps (in d^2 units) below that of rank want-1
+  // cannot reach the first `want` places: they are not fetched at all, and the best of them becomes the cut of the
+  // proof (which then holds by construction).  Typically 5 of 8 candidate rows are read instead of 8 - this kernel
+  // is bound by exactly that L2 traffic.
+  if (nr > KP && want < KP) {
+    const float s_want = s_score[warp][want - 1];
+    const float s_mine = lane < KP ? s_score[warp][lane] : -CUDART_INF_F;
+    const bool keep = lane < want || (my_idx >= 0 && 2.0f * (s_want - s_mine) < 4.0f * eps);
+    const unsigned kept = __ballot_sync(0xffffffffu, lane < KP && my_idx >= 0 && keep);
+    const int n_keep = __popc(kept);                         // ranks are score-sorted: the kept ones are ranks [0, n_keep)
+    if (n_keep < KP && s_idx[warp][n_keep] >= 0) {
+      cut = s_score[warp][n_keep];
+      if (lane >= n_keep) my_idx = -1;
+    }
+  }
   float my_d2 = CUDART_INF_F;
   for (int c = 0; c < KP; ++c) {
     const int r = __shfl_sync(0xffffffffu, my_idx, c);
@@ -311,17 +468,10 @@ knn_verify_kernel(const float* __restrict__ ref, const float* __restrict__ query
     const int oi = __shfl_sync(0xffffffffu, my_idx, c);
     if (oi >= 0 && (od < my_d || (od == my_d && oi < my_idx))) ++rank;
   }
-  const int want = k + (drop_first ? 1 : 0);                // list length the caller needs
-  const int have = (int)min((long long)want, nr);
   // proof that nothing outside the candidate list belongs to the first `have` entries
-  const float cut = cand_cut[q];
   bool proven = true;
   if (nr > KP) {
-    const float qn2 = 2.0f * q_half_norm2[q];
     const float d2_cut = qn2 - 2.0f * cut;                  // approximate d^2 of the best discarded row (lower bound)
-    // |S_gemm - S| <= ~1.2e-5 |q||r| (dropped lo.lo + bf16 rounding of lo + fp32 accumulation);
-    // d^2 carries twice that; |q||r| <= (|q|^2 + max|r|^2)/2; 4x safety factor
-    const float eps = 5e-5f * (qn2 + __uint_as_float(*r_max_norm2_bits));
     // d2 of the candidate ranked have-1
     const unsigned who = __ballot_sync(0xffffffffu, my_idx >= 0 && rank == have - 1);
     const float kth_d2 = __shfl_sync(0xffffffffu, my_d2, who ? __ffs(who) - 1 : 0);
@@ -348,13 +498,31 @@ knn_verify_kernel(const float* __restrict__ ref, const float* __restrict__ query
 int launch_knn_exact(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k, int drop_first,
                      float* dist_out, int32_t* idx_out, const int* qlist, const int* qcount, cudaStream_t stream);
 
+// Number of work units (CTAs or CTA pairs) and of candidate-list slots per query for the stream-K decomposition:
+// equal contiguous ranges of (row tile, reference tile) pairs, at least ceil(NT / 3) pairs each so that no row tile is
+// touched by more than kMaxSlots units.
+struct TcPlan { int units, slots; };
+static TcPlan plan_units(int n_row_tiles, int n_col_tiles, int max_units) {
+  const long long total = (long long)n_row_tiles * n_col_tiles;
+  const long long min_len = (n_col_tiles + 2) / 3;
+  long long units = total / min_len;
+  if (units > max_units) units = max_units;
+  if (units < 1) units = 1;
+  const long long len = total / units;                                 // shortest range
+  long long slots = (n_col_tiles - 1 + len - 1) / len + 1;
+  if (slots > n_col_tiles) slots = n_col_tiles;
+  if (slots > units) slots = units;
+  if (slots > kMaxSlots) slots = kMaxSlots;                           // (cannot happen: len >= ceil(NT / 3))
+  return TcPlan{(int)units, (int)slots};
+}
+
 template <int KP>
 static int run_tc(const float* ref, const float* query, int64_t nr, int64_t nq, int d, int k, int drop_first,
                   float* dist_out, int32_t* idx_out, const __nv_bfloat16* rhi, const __nv_bfloat16* rlo,
-                  const float* rhn, const unsigned int* rmax, __nv_bfloat16* qhi, __nv_bfloat16* qlo, float* qhn, int* cand, float* cut,
+                  const float* rhn, const unsigned int* rmax, const unsigned int* flags, __nv_bfloat16* qhi, __nv_bfloat16* qlo, float* qhn, int* cand, float* cand_score,
                   int* redo_list, int* redo_count, cudaStream_t stream) {
   const int dp = d + kTcBlockK;                      // operand rows carry one extra 64-feature block (see split_rows_kernel)
-  split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(query, nq, d, qhi, qlo, qhn, nullptr, 0);
+  split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(query, nq, d, qhi, qlo, qhn, nullptr, 0, flags);
   note_launch();
   // CTA pairs when every pair gets at least one 256-row tile on most SMs; single CTAs for small query sets
   const int sms = num_sms();
@@ -371,11 +539,15 @@ static int run_tc(const float* ref, const float* query, int64_t nr, int64_t nq, 
   p.n_col_tiles = (int)((nr + kTcBlockN - 1) / kTcBlockN);
   const int tile_rows = kTcBlockM * ctas;
   p.n_row_tiles = (int)((nq + tile_rows - 1) / tile_rows);
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcBlockN >> 3) << 17) | ((uint32_t)(tile_rows >> 4) << 24);
-  p.r_half_norm2 = rhn; p.cand_idx = cand; p.cand_cut = cut;
-  const size_t smem = kTcCtlBytes + 1024 + (ctas == 2 ? (size_t)3 * (2 * kTcQBytes + kTcRBytes) : (size_t)2 * (2 * kTcQBytes + 2 * kTcRBytes));
-  const int units = sms / ctas;
-  const int grid = (p.n_row_tiles < units ? p.n_row_tiles : units) * ctas;
+  p.idesc = (1u << 4) | ((uint32_t)(kTcBlockN >> 3) << 17) | ((uint32_t)(tile_rows >> 4) << 24);   // operand formats: in the kernel
+  p.flags = flags;
+  p.r_half_norm2 = rhn; p.cand_idx = cand; p.cand_score = cand_score;
+  const size_t smem = kTcCtlBytes + 1024 + (ctas == 2 ? (size_t)3 * (2 * kTcQBytes + kTcRBytes) : (size_t)2 * (2 * kTcQBytes + 2 * kTcRBytes)) +
+                      kTcScratchBytes;
+  const TcPlan plan = plan_units(p.n_row_tiles, p.n_col_tiles, sms / ctas);
+  p.n_slots = plan.slots;
+  const int grid = plan.units * ctas;
+  CCAL_CUDA_OK(cudaMemsetAsync(cand, 0xff, (size_t)nq * plan.slots * KP * sizeof(int), stream));   // -1 = empty slot
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kTcThreads);
@@ -398,7 +570,7 @@ static int run_tc(const float* ref, const float* query, int64_t nr, int64_t nq, 
   }
   note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
-  knn_verify_kernel<KP><<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(ref, query, nr, nq, d, k, drop_first, cand, cut, qhn,
+  knn_verify_kernel<KP><<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(ref, query, nr, nq, d, k, drop_first, plan.slots, cand, cand_score, qhn,
                                                                       rmax, dist_out, idx_out, redo_list, redo_count);
   note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
@@ -423,7 +595,7 @@ int knn_l2_tensor(const float* ref, const float* query, int64_t nr, int64_t nq, 
   const size_t dp = (size_t)d + kTcBlockK;
   const size_t o_rhi = take((size_t)nr * dp * bf), o_rlo = take((size_t)nr * dp * bf), o_rhn = take((size_t)nr * 4);
   const size_t o_qhi = take((size_t)chunk * dp * bf), o_qlo = take((size_t)chunk * dp * bf), o_qhn = take((size_t)chunk * 4);
-  const size_t o_cand = take((size_t)chunk * KP * 4), o_cut = take((size_t)chunk * 4);
+  const size_t o_cand = take((size_t)chunk * kMaxSlots * KP * 4), o_cut = take((size_t)chunk * kMaxSlots * KP * 4);
   const size_t o_list = take((size_t)chunk * 4), o_cnt = take(256), o_rmax = take(256);
   AsyncWorkspace workspace;
   CCAL_CUDA_OK(workspace.alloc(off, stream));
@@ -432,8 +604,18 @@ int knn_l2_tensor(const float* ref, const float* query, int64_t nr, int64_t nq, 
   __nv_bfloat16* rlo = (__nv_bfloat16*)(ws + o_rlo);
   float* rhn = (float*)(ws + o_rhn);
   unsigned int* rmax = (unsigned int*)(ws + o_rmax);
-  cudaMemsetAsync(rmax, 0, sizeof(unsigned int), stream);
-  split_rows_kernel<<<(unsigned)((nr + 7) / 8), 256, 0, stream>>>(ref, nr, d, rhi, rlo, rhn, rmax, 1);
+  unsigned int* flags = rmax + 4;
+  cudaMemsetAsync(rmax, 0, 8 * sizeof(unsigned int), stream);
+  // operand mode: are both matrices exactly representable in bf16 / fp16?  (one read pass, HBM-bound)
+  {
+    const int sms = num_sms();
+    long long g = ((long long)nr * d / 4 + 255) / 256;
+    exact16_scan_kernel<<<(int)(g < 8 * sms ? (g < 1 ? 1 : g) : 8 * sms), 256, 0, stream>>>(ref, (long long)nr * d, flags);
+    g = ((long long)nq * d / 4 + 255) / 256;
+    exact16_scan_kernel<<<(int)(g < 8 * sms ? (g < 1 ? 1 : g) : 8 * sms), 256, 0, stream>>>(query, (long long)nq * d, flags);
+    note_launch(2);
+  }
+  split_rows_kernel<<<(unsigned)((nr + 7) / 8), 256, 0, stream>>>(ref, nr, d, rhi, rlo, rhn, rmax, 1, flags);
   note_launch();
   int rc = CCAL_OK;
   for (int64_t q0 = 0; q0 < nq && rc == CCAL_OK; q0 += chunk) {
@@ -443,7 +625,7 @@ int knn_l2_tensor(const float* ref, const float* query, int64_t nr, int64_t nq, 
     float* dptr = dist_out ? dist_out + q0 * k : nullptr;
     int32_t* iptr = idx_out ? idx_out + q0 * k : nullptr;
 #define CCAL_RUN_TC(KPV)                                                                                       \
-  rc = run_tc<KPV>(ref, query + q0 * d, nr, m, d, k, drop_first, dptr, iptr, rhi, rlo, rhn, rmax,               \
+  rc = run_tc<KPV>(ref, query + q0 * d, nr, m, d, k, drop_first, dptr, iptr, rhi, rlo, rhn, rmax, flags,        \
                    (__nv_bfloat16*)(ws + o_qhi), (__nv_bfloat16*)(ws + o_qlo), (float*)(ws + o_qhn),            \
                    (int*)(ws + o_cand), (float*)(ws + o_cut), (int*)(ws + o_list), cnt, stream)
     if (KP == 8) CCAL_RUN_TC(8); else if (KP == 16) CCAL_RUN_TC(16); else CCAL_RUN_TC(24);

@@ -195,12 +195,18 @@ def test_dac_fit_k_larger_than_base_and_duplicates(cuda_lib):
 
 @pytest.mark.parametrize("nr,nq,d,k,drop", [(1000, 5000, 512, 5, False), (3000, 3000, 768, 10, True), (257, 4100, 64, 16, False),
                                              (10000, 2048, 512, 1, False)])
-def test_knn_tensor_core_filter_equals_exhaustive_scan(cuda_lib, nr, nq, d, k, drop):
+@pytest.mark.parametrize("stored_as", [None, torch.bfloat16, torch.float16], ids=["fp32", "bf16_values", "fp16_values"])
+def test_knn_tensor_core_filter_equals_exhaustive_scan(cuda_lib, nr, nq, d, k, drop, stored_as):
     """ccal_knn_l2 (tcgen05 GEMM filter + exact verification + exhaustive redo of unproven rows) must
-    return what the exhaustive fp32 scan returns."""
+    return what the exhaustive fp32 scan returns - in all three operand modes of the filter: general fp32 values
+    (bf16 hi/lo split, three MMAs), values that are exactly bf16 and values that are exactly fp16 (one MMA)."""
     g = torch.Generator(device="cuda").manual_seed(nr + nq)
     ref = torch.nn.functional.normalize(torch.randn(nr, d, device="cuda", generator=g) + 2.0, dim=-1)
-    qry = ref if drop else torch.nn.functional.normalize(torch.randn(nq, d, device="cuda", generator=g) + 2.0, dim=-1)
+    qry = None if drop else torch.nn.functional.normalize(torch.randn(nq, d, device="cuda", generator=g) + 2.0, dim=-1)
+    if stored_as is not None:              # features cached in a 16-bit dtype (the reference's default is fp16)
+        ref = ref.to(stored_as).float()
+        qry = None if drop else qry.to(stored_as).float()
+    qry = ref if drop else qry
     d_tc, i_tc = native.knn_l2(ref, qry, k, drop)
     d_ex, i_ex = native.knn_l2(ref, qry, k, drop, exhaustive=True)
     torch.testing.assert_close(d_tc, d_ex, rtol=2e-6, atol=2e-7)
