@@ -90,6 +90,23 @@ def quantile_thresholds(keys: torch.Tensor, n_bins: int, quantile_method: str = 
     return edges[1:-1]
 
 
+def uniform_thresholds_of(keys: torch.Tensor, n_bins: int, group=None) -> np.ndarray:
+    """Inner bin edges of KBinsDiscretizer(n_bins, strategy='uniform') fitted on the float32 column `keys`:
+    np.linspace(min, max, n_bins + 1)[1:-1] evaluated in float32 as scikit-learn 1.9 does (bin = number of edges <= x);
+    empty for a constant column (one bin).  min / max come from the device (global over `group`)."""
+    n = keys.numel()
+    if group is not None:
+        cnt = torch.tensor([n], dtype=torch.int64, device=keys.device)
+        torch.distributed.all_reduce(cnt, group=group)
+        n = int(cnt.item())
+    if n == 0:
+        return np.zeros(0, np.float64)
+    lo, hi = native.order_statistics(keys, [0, n - 1], group=group)
+    if lo == hi:
+        return np.zeros(0, np.float64)
+    return np.linspace(np.float32(lo), np.float32(hi), int(n_bins) + 1)[1:-1].astype(np.float64)
+
+
 def AdaptiveECE(conf, pred, gt, conf_bin_num=10, quantile_method="averaged_inverted_cdf", group=None):
     """Equal-mass-bin ECE, reference tools/metrics.py:212-236."""
     c = _conf_dev(conf)
@@ -102,12 +119,19 @@ def AdaptiveECE(conf, pred, gt, conf_bin_num=10, quantile_method="averaged_inver
 
 def PIECE(conf, knndist, pred, gt, dist_bin_num=10, conf_bin_num=10, knn_strategy="quantile",
           quantile_method="averaged_inverted_cdf", group=None):
-    """Proximity-informed ECE, reference tools/metrics.py:132-178: groups = (quantile bin of
-    knndist) x (uniform inner-edge bin of conf)."""
-    if knn_strategy != "quantile":
-        raise ValueError("only knn_strategy='quantile' (the reference default and only caller) is supported")
+    """Proximity-informed ECE, reference tools/metrics.py:132-178: groups = (bin of knndist) x (uniform
+    inner-edge bin of conf).  knn_strategy (reference :152, handed to KBinsDiscretizer): "quantile" (the default and
+    the reference's only caller) = exact global order statistics; "uniform" = np.linspace(min, max, bins + 1) in
+    float32 like scikit-learn on a float32 column (min / max are order statistics 0 and N-1, global over `group`).
+    "kmeans" (scikit-learn's 1-D Lloyd iterations) is not provided."""
+    if knn_strategy not in ("quantile", "uniform"):
+        raise ValueError(f"knn_strategy={knn_strategy!r}: 'quantile' and 'uniform' are supported; 'kmeans' "
+                         "(scikit-learn's KMeans on the proximity column) is not")
     key2 = _dev(knndist, torch.float32)
-    thr2 = quantile_thresholds(key2, dist_bin_num, quantile_method, group)
+    if knn_strategy == "quantile":
+        thr2 = quantile_thresholds(key2, dist_bin_num, quantile_method, group)
+    else:
+        thr2 = uniform_thresholds_of(key2, dist_bin_num, group)
     thr = np.linspace(0, 1, int(conf_bin_num) + 1)[1:-1]
     if len(thr2) == 0:
         table = native.bin_stats(_conf_dev(conf), _pred_dev(pred), _dev(gt, torch.int64), thr)

@@ -206,12 +206,23 @@ def adaptive_ece(conf, pred, gt, n_bins: int = 10, method: str = "averaged_inver
     return float(_grouped_gap(which, conf, (pred == gt)).sum())
 
 
+def uniform_bin_ids(x, n_bins: int) -> np.ndarray:
+    """KBinsDiscretizer(strategy='uniform', encode='ordinal') on one column (scikit-learn 1.9
+    preprocessing/_discretization.py): edges = np.linspace(min, max, n_bins + 1) in the column's own dtype,
+    bin = searchsorted(edges[1:-1], x, side='right'); a constant column collapses to one bin."""
+    x = np.asarray(x)
+    if x.min() == x.max():
+        return np.zeros(len(x), np.int64)
+    edges = np.linspace(x.min(), x.max(), n_bins + 1)
+    return np.searchsorted(edges[1:-1], x, side="right")
+
+
 def piece(conf, knndist, pred, gt, dist_bin_num: int = 10, conf_bin_num: int = 10,
-          method: str = "averaged_inverted_cdf") -> float:
-    """tools/metrics.py:132-178 with knn_strategy='quantile': 2-D groups
-    (quantile bin of knndist) x (uniform inner-edge bin of conf)."""
+          method: str = "averaged_inverted_cdf", knn_strategy: str = "quantile") -> float:
+    """tools/metrics.py:132-178: 2-D groups (quantile - the default - or uniform bin of knndist) x
+    (uniform inner-edge bin of conf)."""
     conf, pred, gt, knndist = map(np.asarray, (conf, pred, gt, knndist))
-    kb = quantile_bin_ids(knndist, dist_bin_num, method)
+    kb = quantile_bin_ids(knndist, dist_bin_num, method) if knn_strategy == "quantile" else uniform_bin_ids(knndist, dist_bin_num)
     cb = np.digitize(conf, np.linspace(0, 1, conf_bin_num + 1)[1:-1])
     return float(_grouped_gap(kb * (conf_bin_num + 1) + cb, conf, (pred == gt)).sum())
 

@@ -166,6 +166,9 @@ def proximity_and_piece():
         p = ref_metrics.PIECE(conf, prox, pred, case.labels, nb, 10)
         assert abs(orc.piece(conf, prox, pred, case.labels, nb, 10) - p) < 3e-8
         out[f"piece{nb}"] = float(p)
+        pu = ref_metrics.PIECE(conf, prox, pred, case.labels, nb, 10, knn_strategy="uniform")      # tools/metrics.py:152
+        assert abs(orc.piece(conf, prox, pred, case.labels, nb, 10, knn_strategy="uniform") - pu) < 3e-8
+        out[f"piece{nb}_uniform"] = float(pu)
     np.savez_compressed(os.path.join(OUT, "proximity_piece.npz"), **out)
     print("proximity_piece: piece10=%.8f" % out["piece10"])
 

@@ -95,6 +95,12 @@ def test_piece_matches_reference(cuda_lib, golden):
     prox = np.exp(-np.mean(g["knn"], axis=-1))
     for nb in (10, 5):
         assert abs(metrics.PIECE(g["conf"], prox, g["pred"], g["labels"], nb, 10) - float(g[f"piece{nb}"])) < 1e-7
+        assert abs(metrics.PIECE(g["conf"], prox, g["pred"], g["labels"], nb, 10, knn_strategy="uniform")
+                   - float(g[f"piece{nb}_uniform"])) < 1e-7
+    assert metrics.PIECE(g["conf"], np.full(len(prox), 0.5, np.float32), g["pred"], g["labels"], 10, 10, knn_strategy="uniform") \
+        == metrics.ECE(g["conf"], g["pred"], g["labels"], 10)           # constant proximity: one proximity bin
+    with pytest.raises(ValueError, match="kmeans"):
+        metrics.PIECE(g["conf"], prox, g["pred"], g["labels"], 10, 10, knn_strategy="kmeans")
 
 
 # ----------------------------------------------------------------------------- K1

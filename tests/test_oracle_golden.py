@@ -61,6 +61,8 @@ def test_proximity_and_piece(golden):
     prox = np.exp(-np.mean(g["knn"], axis=-1))
     for nb in (10, 5):
         assert abs(orc.piece(g["conf"], prox, g["pred"], g["labels"], nb, 10) - float(g[f"piece{nb}"])) < 3e-8
+        assert abs(orc.piece(g["conf"], prox, g["pred"], g["labels"], nb, 10, knn_strategy="uniform")
+                   - float(g[f"piece{nb}_uniform"])) < 3e-8
 
 
 def test_ts_loss_grad_against_finite_difference():
