@@ -207,18 +207,23 @@ __device__ __forceinline__ void trace_exit(int kind, unsigned long long t0, long
 }
 
 // Class ranges per row tile of the redo (gather) kernel, derived on the device from the length of the redo list:
-// the smallest S within 2 % of the best wave efficiency, every range at least 4 text tiles long.  The finish
+// the S that minimises a two-term cost model (below), every range at least 4 text tiles long.  The finish
 // kernel evaluates the same function, so both agree without a host round trip.
 __host__ __device__ inline int gather_splits(int n_listed, int tile_rows, int n_units, int n_col_tiles, int split_cap) {
   const int n_row_tiles = (n_listed + tile_rows - 1) / tile_rows;
   int S = 1;
   if (n_row_tiles > 0 && n_listed <= split_cap) {
+    // time of the launch in text-tile units: waves x (text tiles per unit + the unit's fixed cost).  The fixed cost is
+    // the by-index gather of the unit's image rows by one warp - measured at ~100 us, the MMA time of ~32 text tiles
+    // at d = 512 - so cutting tiles into class ranges only pays when the row tiles leave most SMs without work
+    // (62 row tiles on 74 pairs: S = 1 takes 0.63 ms where the wave-efficiency rule's S = 7 took 1.27 ms).
+    constexpr int kUnitCost = 32;
     const int s_max = n_col_tiles / 4 < 32 ? (n_col_tiles / 4 < 1 ? 1 : n_col_tiles / 4) : 32;
-    float best = 0.f;
+    long long best = -1;
     for (int s = 1; s <= s_max; ++s) {
-      const int units = n_row_tiles * s, waves = (units + n_units - 1) / n_units;
-      const float eff = (float)units / (float)(waves * n_units);
-      if (eff > best + 0.02f) { best = eff; S = s; }
+      const long long units = (long long)n_row_tiles * s, waves = (units + n_units - 1) / n_units;
+      const long long cost = waves * ((n_col_tiles + s - 1) / s + kUnitCost);
+      if (best < 0 || cost < best) { best = cost; S = s; }
     }
   }
   return S;
@@ -1031,13 +1036,46 @@ static bool guess_pipeline_applies(int mode, int64_t n, int c, int d, int dtype,
   return n >= (int64_t)kBlockM * 2 * (num_sms() / 2) && (double)n * (double)c >= 1.0e9;
 }
 
+// development aid (CCAL_SCORE_TIMELINE=1): CUDA events between the pipeline's kernels, printed after a stream sync
+struct Timeline {
+  bool on;
+  cudaStream_t stream;
+  int n = 0;
+  cudaEvent_t ev[16];
+  const char* name[16];
+  Timeline(cudaStream_t s) : on(getenv("CCAL_SCORE_TIMELINE") != nullptr), stream(s) {}
+  void mark(const char* what) {
+    if (!on || n >= 16) return;
+    cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n], stream);
+    name[n++] = what;
+  }
+  void report() {
+    if (!on) return;
+    cudaStreamSynchronize(stream);
+    fprintf(stderr, "ccal timeline:");
+    for (int i = 1; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, " %s %.3f", name[i], ms);
+    }
+    float tot = 0.f;
+    if (n > 1) cudaEventElapsedTime(&tot, ev[0], ev[n - 1]);
+    fprintf(stderr, " | total %.3f ms\n", tot);
+    for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+  }
+};
+
 static int launch_guess_verify(const void* img, const void* txt, int64_t n, int c, int d, int dtype, ScoreParams p,
                                const ThrBlock& thr, cudaStream_t stream) {
   constexpr int ctas = 2;
+  Timeline tl(stream);
+  tl.mark("start");
   const int units = num_sms() / ctas;
   const int tile_rows = kBlockM * ctas;
   const int n_col_tiles = (c + kBlockN - 1) / kBlockN;
-  const int split_cap = 32768;
+  int split_cap = 32768;
+  if (const char* e = getenv("CCAL_REDO_SPLIT_CAP")) split_cap = atoi(e);       // development aid
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   const size_t o_qi = take((size_t)n * d), o_qt = take((size_t)c * d), o_inv = take((size_t)n * 4);
@@ -1073,6 +1111,7 @@ static int launch_guess_verify(const void* img, const void* txt, int64_t n, int 
   }
   note_launch(3);
   CCAL_CUDA_OK(cudaGetLastError());
+  tl.mark("quant");
 
   int rc;
   p.n = n; p.c = c; p.d = d;
@@ -1099,6 +1138,7 @@ static int launch_guess_verify(const void* img, const void* txt, int64_t n, int 
     a.part_max = row_max; a.part_arg = guess; a.row_scale_inv = inv_scale;
     a.pred_out = nullptr; a.conf_out = nullptr; a.rowmax_out = nullptr; a.table = nullptr;
     if ((rc = launch_variant<2, true, 0, false, true, false>(map_i8, map_t8, map_i8, map_t8, a, thr, grid_rows, pl.smem, stream))) return rc;
+    tl.mark("guess");
   }
   // ---- exact bf16 logit of every row's guessed class (overwrites the FP8 estimate of the row maximum)
   {
@@ -1111,6 +1151,7 @@ static int launch_guess_verify(const void* img, const void* txt, int64_t n, int 
         map_img128, (const unsigned char*)txt, guess, (long long)n, c, d, d / kBlockK, idesc128, row_max);
     note_launch();
     CCAL_CUDA_OK(cudaGetLastError());
+    tl.mark("guess_logit");
   }
   // ---- kernel B: bf16 pass 2 at the guessed multiplier + exact max / argmax; mismatches -> redo list
   p.kblocks = d / kBlockK;
@@ -1126,6 +1167,7 @@ static int launch_guess_verify(const void* img, const void* txt, int64_t n, int 
     if (pl.resident) rc = launch_variant<2, true, 2, false>(map_img, map_txt, map_img, map_txt, b, thr, grid_rows, pl.smem, stream);
     else rc = launch_variant<2, false, 2, false>(map_img, map_txt, map_img, map_txt, b, thr, grid_rows, pl.smem, stream);
     if (rc) return rc;
+    tl.mark("verify");
   }
   // ---- redo: pass 2 for the listed rows at the multiplier of their exact argmax
   {
@@ -1137,13 +1179,16 @@ static int launch_guess_verify(const void* img, const void* txt, int64_t n, int 
     r.split_cap = split_cap;
     r.part_sum = (float*)(ws + o_part);
     if ((rc = launch_variant<2, true, 0, false, false, true>(map_img, map_txt, map_img, map_txt, r, thr, units * ctas, pl.smem, stream))) return rc;
+    tl.mark("redo");
     split_finish_kernel<<<num_sms(), 256, 0, stream>>>(r.part_sum, row_max, guess, 0, n_col_tiles, p.scale, nullptr, p.pred_out, p.conf_out,
                                                       p.rowmax_out, p.labels, thr, p.n_thr, p.table, redo_rows, redo_count,
                                                       tile_rows, units, split_cap);
     guess_stats_kernel<<<1, 32, 0, stream>>>((long long)n, redo_count);
     note_launch(2);
     CCAL_CUDA_OK(cudaGetLastError());
+    tl.mark("finish");
   }
+  tl.report();
   return CCAL_OK;
 }
 
