@@ -1005,6 +1005,166 @@ guess_logit_kernel(const __grid_constant__ CUtensorMap map_img, const unsigned c
   if (warp == 0) ptx::tmem_dealloc(tmem_base, 128);
 }
 
+// The same computation as a PERSISTENT, software-pipelined kernel (what the pipeline launches): one CTA per SM walks
+// 128-row tiles; a six-stage ring of {image slab by TMA, gathered text slab by cp.async} keeps ~100 KB of loads in
+// flight per SM, so the kernel runs at memory speed instead of paying the load latency once per round per CTA
+// (guess_logit_kernel above: 0.54 ms at 1M x 512, 1.4 ms at 1.75M x 768; this one: see profiles/).
+//   warp 0      TMA producer of the image slabs
+//   warp 1      TMEM allocator + MMA issuer (128 x 128 x 16, two 128-column accumulator stages)
+//   warps 2-5   thread r gathers the text row of image row r's guessed class (cp.async, three slabs in flight, then a
+//               writer-side proxy fence and one arrive per warp), and reads the diagonal of the PREVIOUS tile
+// The arithmetic is that of guess_logit_kernel and of the scoring kernels: K ascending in steps of 16 into one fp32
+// TMEM accumulator.
+constexpr int kDiagPThreads = 192;
+constexpr int kDiagPStages = 6;
+constexpr int kDiagPLookahead = 3;
+struct __align__(16) DiagCtl {
+  uint64_t full[kDiagPStages];
+  uint64_t empty[kDiagPStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kDiagPThreads, 1)
+guess_logit_persistent_kernel(const __grid_constant__ CUtensorMap map_img, const unsigned char* __restrict__ txt,
+                              const int* __restrict__ guess, long long n, int c, int d, int kblocks, uint32_t idesc,
+                              float* __restrict__ out) {
+  extern __shared__ unsigned char smem_dyn[];
+  DiagCtl* ctl = reinterpret_cast<DiagCtl*>(smem_dyn);
+  const uint32_t base = (ptx::smem_u32(smem_dyn) + 1024u + 1023u) & ~1023u;       // ring: [stage][A slab | B slab]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n_tiles = (n + kBlockM - 1) / kBlockM;
+  constexpr uint32_t kStageBytes = 2 * kASlabBytes;
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&map_img);
+    for (int i = 0; i < kDiagPStages; ++i) { ptx::mbar_init(&ctl->full[i], 1 + 4); ptx::mbar_init(&ctl->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&ctl->acc_full[i], 1); ptx::mbar_init(&ctl->acc_empty[i], 4); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc(&ctl->tmem_base, 256); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    uint32_t stage = 0, phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::mbar_wait(&ctl->empty[stage], phase ^ 1u);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&ctl->full[stage], kASlabBytes);
+          ptx::tma_load_2d(smem_dyn + (base - ptx::smem_u32(smem_dyn)) + (size_t)stage * kStageBytes, &map_img, &ctl->full[stage],
+                           kb * kBlockK, (int)(tile * kBlockM), ptx::kEvictFirst);
+        }
+        __syncwarp();
+        if (++stage == kDiagPStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1u;
+      ptx::mbar_wait_short(&ctl->acc_empty[as], ((it >> 1) & 1u) ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * 128u;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::mbar_wait_short(&ctl->full[stage], phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t a_desc = ptx::make_kmajor_sw128_desc(base + stage * kStageBytes);
+          const uint64_t b_desc = ptx::make_kmajor_sw128_desc(base + stage * kStageBytes + kASlabBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            ptx::umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+          ptx::umma_commit(&ctl->empty[stage]);
+          if (kb == kblocks - 1) ptx::umma_commit(&ctl->acc_full[as]);
+        }
+        __syncwarp();
+        if (++stage == kDiagPStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    const int r = (warp & 3) * 32 + lane;                       // TMEM lane = image row within the tile = B row
+    uint32_t stage = 0, phase = 0;                              // ring position of the slab being ISSUED
+    uint32_t a_stage = 0;                                       // ring position of the slab being ANNOUNCED
+    int in_flight = 0;
+    uint32_t it = 0;
+    long long prev_row = -1;
+    auto announce = [&]() {                                     // the oldest issued slab has landed: hand it to the MMA warp
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&ctl->full[a_stage]);
+      if (++a_stage == kDiagPStages) a_stage = 0;
+      --in_flight;
+    };
+    auto epilogue = [&](uint32_t j, long long row) {            // diagonal of accumulator stage j & 1 -> out[row]
+      const uint32_t as = j & 1u;
+      ptx::mbar_wait(&ctl->acc_full[as], (j >> 1) & 1u);
+      ptx::tc_fence_after();
+      uint32_t raw[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + as * 128u + (uint32_t)((warp & 3) * 32), raw);
+      ptx::tmem_ld_wait(raw);
+      float x = 0.f;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) x = (q == lane) ? __uint_as_float(raw[q]) : x;
+      if (row >= 0 && row < n) out[row] = x;
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&ctl->acc_empty[as]);
+    };
+    long long tile = blockIdx.x;
+    int g = 0;
+    if (tile < n_tiles) { const long long row = tile * kBlockM + r; g = row < n ? __ldg(guess + row) : 0; }
+    // Copy mapping: eight consecutive lanes fetch the eight 16-byte chunks of ONE text row's 128-byte slab line, so a
+    // warp instruction touches 4 lines instead of 32 (lane = row would be one L1 wavefront per lane); eight
+    // instructions cover the warp's 32 rows.  The row pointers travel by shuffle from the lane that owns the row.
+    const int sub = lane >> 3, q = lane & 7;
+    for (; tile < n_tiles; tile += gridDim.x, ++it) {
+      const long long row = tile * kBlockM + r;
+      const unsigned long long mine = reinterpret_cast<unsigned long long>(txt + (size_t)min(max(g, 0), c - 1) * (size_t)d * 2);
+      const unsigned char* src[8];
+      uint32_t dst[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + sub;                               // row within this warp's 32
+        src[i] = reinterpret_cast<const unsigned char*>(__shfl_sync(0xffffffffu, mine, rr)) + q * 16;
+        const int rt = (warp & 3) * 32 + rr;                      // row within the tile
+        dst[i] = base + kASlabBytes + (uint32_t)rt * 128u + (uint32_t)((q ^ (rt & 7)) << 4);
+      }
+      const long long next = tile + gridDim.x;                  // next tile's guess: its latency hides under this tile
+      int g_next = 0;
+      if (next < n_tiles) { const long long nr = next * kBlockM + r; g_next = nr < n ? __ldg(guess + nr) : 0; }
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::mbar_wait(&ctl->empty[stage], phase ^ 1u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ptx::cp_async_16(dst[i] + stage * kStageBytes, src[i] + (size_t)kb * 128);
+        ptx::cp_async_commit();
+        if (++stage == kDiagPStages) { stage = 0; phase ^= 1u; }
+        if (++in_flight > kDiagPLookahead) { ptx::cp_async_wait<kDiagPLookahead>(); announce(); }
+      }
+      if (kblocks <= kDiagPLookahead) {        // narrow features: the previous tile's last slabs may still be unannounced,
+        ptx::cp_async_wait<0>();                //   and its accumulator cannot complete before they are
+        while (in_flight > 0) announce();
+      }
+      if (it > 0) epilogue(it - 1, prev_row);
+      prev_row = row;
+      g = g_next;
+    }
+    // drain: the last slabs, then the last tile's diagonal
+    if (in_flight > 2) { ptx::cp_async_wait<2>(); announce(); }
+    if (in_flight > 1) { ptx::cp_async_wait<1>(); announce(); }
+    if (in_flight > 0) { ptx::cp_async_wait<0>(); announce(); }
+    if (it > 0) epilogue(it - 1, prev_row);
+  }
+  __syncwarp();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+}
+
 __device__ unsigned long long g_guess_stats[2];            // {rows scored through the FP8-guess pipeline, rows redone}
 __global__ void guess_stats_kernel(long long n, const int* __restrict__ redo_count) {
   if (threadIdx.x == 0) { atomicAdd(&g_guess_stats[0], (unsigned long long)n); atomicAdd(&g_guess_stats[1], (unsigned long long)*redo_count); }
@@ -1144,11 +1304,20 @@ static int launch_guess_verify(const void* img, const void* txt, int64_t n, int 
   {
     CUtensorMap map_img128;
     if ((rc = make_map(&map_img128, img, n, d, kBlockM, dtype))) return rc;
-    const size_t smem = 1024 + (size_t)2 * kDiagSlabs * kASlabBytes;
-    CCAL_CUDA_OK(cudaFuncSetAttribute(guess_logit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t idesc128 = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    guess_logit_kernel<<<(unsigned)((n + kBlockM - 1) / kBlockM), kDiagThreads, smem, stream>>>(
-        map_img128, (const unsigned char*)txt, guess, (long long)n, c, d, d / kBlockK, idesc128, row_max);
+    const long long n_tiles = (n + kBlockM - 1) / kBlockM;
+    if (getenv("CCAL_DIAG_SIMPLE")) {                     // development aid: the one-tile-per-CTA form
+      const size_t smem = 1024 + (size_t)2 * kDiagSlabs * kASlabBytes;
+      CCAL_CUDA_OK(cudaFuncSetAttribute(guess_logit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      guess_logit_kernel<<<(unsigned)n_tiles, kDiagThreads, smem, stream>>>(
+          map_img128, (const unsigned char*)txt, guess, (long long)n, c, d, d / kBlockK, idesc128, row_max);
+    } else {
+      const size_t smem = 2048 + (size_t)kDiagPStages * 2 * kASlabBytes;
+      CCAL_CUDA_OK(cudaFuncSetAttribute(guess_logit_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+      guess_logit_persistent_kernel<<<grid, kDiagPThreads, smem, stream>>>(
+          map_img128, (const unsigned char*)txt, guess, (long long)n, c, d, d / kBlockK, idesc128, row_max);
+    }
     note_launch();
     CCAL_CUDA_OK(cudaGetLastError());
     tl.mark("guess_logit");
