@@ -46,6 +46,7 @@ import torch
 METRIC = "calibrated images/sec (GEMM+DAC+softmax+ECE)"
 UNIT = "images/s"
 LOGIT_SCALE, N_BINS = 100.0, 10
+CLOCK_SAMPLE_MS = 200          # nvidia-smi sampling period during the timed region (B200_PROFILING.md's clocks line)
 
 
 @dataclass(frozen=True)
@@ -94,15 +95,16 @@ class ClockSampler:
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, period_ms: int = 200):
         self.gpu_index = gpu_index
+        self.period_ms = int(period_ms)
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu_index), "-lms", "100"],
+                                          "-i", str(self.gpu_index), "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -457,7 +459,7 @@ def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2
     # ---------------- device-resident number
     for _ in range(warmup):
         step()
-    sampler = ClockSampler(ctx.local_rank) if (want_clocks and rank == 0) else None
+    sampler = ClockSampler(ctx.local_rank, CLOCK_SAMPLE_MS) if (want_clocks and rank == 0 and CLOCK_SAMPLE_MS > 0) else None
     if sampler:
         sampler.start()
     native.score_trace(reset=True)
@@ -626,6 +628,7 @@ def dist_check(ctx: Ctx):
 
 
 def main():
+    global CLOCK_SAMPLE_MS
     out = _StdoutToStderr()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -634,9 +637,12 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline workload only (no in21k / strong / dist check)")
+    ap.add_argument("--clock-sample-ms", type=int, default=CLOCK_SAMPLE_MS,
+                    help="nvidia-smi sampling period inside the timed region (0 = no sampling; development aid)")
     ap.add_argument("--workload", default="openvocab", choices=sorted(WORKLOADS),
                     help="BASELINE.json config shape (default: the headline open-vocabulary workload)")
     args = ap.parse_args()
+    CLOCK_SAMPLE_MS = args.clock_sample_ms
     w = WORKLOADS[args.workload]
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3
