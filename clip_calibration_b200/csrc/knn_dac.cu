@@ -9,6 +9,7 @@
 // entry per lane: an insert is one ballot (rank) + one shuffle (shift).
 // Ties: lower reference index first.
 #include "ccal_common.cuh"
+#include <mutex>
 
 #include <cuda_fp16.h>
 #include <math_constants.h>
@@ -762,6 +763,22 @@ extern "C" int ccal_knn_l2_exhaustive(const float* ref, const float* query, int6
   return launch_knn_exact(ref, query, nr, nq, d, k, drop_first, dist_out, idx_out, nullptr, nullptr, (cudaStream_t)stream);
 }
 
+// One library-owned non-blocking stream per device for the second kNN chain of ccal_dac_fit (created on first use,
+// never destroyed; CCAL_DAC_ONE_STREAM=1 keeps everything on the caller's stream).
+static cudaStream_t fit_side_stream() {
+  static std::mutex mu;
+  static cudaStream_t streams[64] = {};
+  if (getenv("CCAL_DAC_ONE_STREAM")) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (streams[dev] == nullptr && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) {
+    streams[dev] = nullptr;
+    cudaGetLastError();
+  }
+  return streams[dev];
+}
+
 extern "C" int ccal_dac_fit(const float* base_zs, const float* cur_zs, const float* base_tuned,
                             const float* cur_tuned, int b, int c, int d, int k,
                             float* class_conf_out, int32_t* knn_idx_zs_out, int32_t* knn_idx_tuned_out,
@@ -777,10 +794,32 @@ extern "C" int ccal_dac_fit(const float* base_zs, const float* cur_zs, const flo
   if (small_fit_applies(b, c, d))
     return launch_dac_fit_small(base_zs, cur_zs, base_tuned, cur_tuned, b, c, d, k, class_conf_out, knn_idx_zs_out,
                                 knn_idx_tuned_out, knn_dist_zs_out, knn_dist_tuned_out, stream);
-  int rc = launch_knn(base_zs, cur_zs, b, c, d, k, 0, knn_dist_zs_out, knn_idx_zs_out, stream);
-  if (rc) return rc;
-  rc = launch_knn(base_tuned, cur_tuned, b, c, d, k, 0, knn_dist_tuned_out, knn_idx_tuned_out, stream);
-  if (rc) return rc;
+  // The two kNN problems (zero-shot space, tuned space) are independent chains of ~9 launches each, several of them
+  // short or narrow (operand scan, split, verify, the redo of a handful of rows): they run on two streams - the
+  // caller's and a library-owned one, forked and joined by events - so that one chain's narrow kernels run underneath
+  // the other's tensor-core filter.  Still one asynchronous unit of work on the caller's stream.
+  cudaStream_t side = fit_side_stream();
+  int rc;
+  if (side != nullptr) {
+    cudaEvent_t fork, join;
+    CCAL_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    CCAL_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    CCAL_CUDA_OK(cudaEventRecord(fork, stream));
+    CCAL_CUDA_OK(cudaStreamWaitEvent(side, fork, 0));
+    rc = launch_knn(base_tuned, cur_tuned, b, c, d, k, 0, knn_dist_tuned_out, knn_idx_tuned_out, side);
+    int rc2 = launch_knn(base_zs, cur_zs, b, c, d, k, 0, knn_dist_zs_out, knn_idx_zs_out, stream);
+    cudaEventRecord(join, side);                    // joined even on failure: the side stream must not outlive the call
+    cudaStreamWaitEvent(stream, join, 0);
+    cudaEventDestroy(fork);
+    cudaEventDestroy(join);
+    if (rc) return rc;
+    if (rc2) return rc2;
+  } else {
+    rc = launch_knn(base_zs, cur_zs, b, c, d, k, 0, knn_dist_zs_out, knn_idx_zs_out, stream);
+    if (rc) return rc;
+    rc = launch_knn(base_tuned, cur_tuned, b, c, d, k, 0, knn_dist_tuned_out, knn_idx_tuned_out, stream);
+    if (rc) return rc;
+  }
   const int kk = k < b ? k : b;
   dac_map_kernel<<<(c + 127) / 128, 128, 0, stream>>>(knn_dist_zs_out, knn_dist_tuned_out, c, k, kk, class_conf_out);
   note_launch();
