@@ -6,6 +6,8 @@ Nothing here computes on the CPU or through ATen kernels, and nothing falls back
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional, Sequence
 
 import numpy as np
@@ -134,6 +136,19 @@ def score_trace(reset: bool = False) -> dict:
             res[name] = {"launches": launches, "ms_per_launch": span / launches * 1e-6,
                          "sm_mhz": (cycles / busy * 1e3) if busy else None}
     return res
+
+
+def guess_pipeline_applies(n: int, c: int, d: int, dtype) -> bool:
+    """Would ccal_score_fused take the FP8-guess -> bf16-verify -> redo pipeline for this shard (csrc/score_fused.cu,
+    guess_pipeline_applies)?  Callers that could split a call into ccal_score_pass1 / ccal_score_pass2 (two bf16
+    passes) use this to keep large shards on the cheaper one-call path."""
+    env = os.environ.get("CCAL_SCORE_FP8", "")
+    if dtype not in (torch.bfloat16, torch.float16) or d % 128 != 0 or d > 768 or c < 512 or env[:1] == "0":
+        return False
+    if env[:1] == "1":
+        return True
+    return n >= 128 * 2 * (torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count // 2) \
+        and float(n) * float(c) >= 1.0e9
 
 
 def score_pass1(img: torch.Tensor, txt: torch.Tensor):

@@ -289,9 +289,11 @@ class CalibratedScorer:
             labels = (labels if isinstance(labels, torch.Tensor) else torch.from_numpy(np.asarray(labels)))
             labels = labels.to(device=self.device, dtype=torch.int64)
         use_table = labels is not None and accumulate
-        if self._fit_done is not None and self.operand_dtype in (torch.float16, torch.bfloat16) and img.shape[0]:
+        if self._fit_done is not None and self.operand_dtype in (torch.float16, torch.bfloat16) and img.shape[0] \
+                and not native.guess_pipeline_applies(img.shape[0], self.txt.shape[0], img.shape[1], img.dtype):
             # the DAC fit is still running on its side stream (from_dac(overlap_fit=True)): pass 1 needs no
             # multipliers and runs underneath it; pass 2 waits for the fit.  Bit-identical to the fused launch.
+            # (Large shards stay on the one-call path: its FP8 guess pass costs half a bf16 pass 1.)
             dotmax, pred = native.score_pass1(img, self.txt)
             self._await_fit()
             conf = native.score_pass2(img, self.txt, dotmax, pred, self.class_conf, self.logit_scale, labels,

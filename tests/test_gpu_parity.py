@@ -981,3 +981,22 @@ def test_pipelined_evaluation_loop_equals_blocking_steps(cuda_lib):
             assert np.array_equal(p.result(), blocking[i])
             assert p.ready() and p.result() is p.result()
     assert tm.total_count(blocking[0]) == 6000
+
+
+def test_guess_pipeline_predicate_matches_the_library(cuda_lib, monkeypatch):
+    """native.guess_pipeline_applies (used by CalibratedScorer.score to keep large shards on the one-call path) must
+    agree with what ccal_score_fused actually does, as seen through the pipeline's own row counter."""
+    for n, c, d, forced in [(3000, 2048, 512, None), (3000, 2048, 512, "1"), (3000, 300, 512, "1"), (3000, 2048, 192, "1"),
+                            (40_000, 30_000, 128, None), (40_000, 20_000, 128, None), (40_000, 30_000, 128, "0")]:
+        if forced is None:
+            monkeypatch.delenv("CCAL_SCORE_FP8", raising=False)
+        else:
+            monkeypatch.setenv("CCAL_SCORE_FP8", forced)
+        img, txt, labels, cc = _device_case(n, c, d, 0.3, torch.bfloat16, seed=n + c + d)
+        native.score_guess_stats(reset=True)
+        native.score_fused(img, txt, cc, 100.0)
+        rows, _ = native.score_guess_stats(reset=True)
+        assert (rows == n) == native.guess_pipeline_applies(n, c, d, torch.bfloat16), (n, c, d, forced, rows)
+        assert rows in (0, n)
+    monkeypatch.delenv("CCAL_SCORE_FP8", raising=False)
+    assert not native.guess_pipeline_applies(10 ** 6, 49408, 512, torch.float32)
