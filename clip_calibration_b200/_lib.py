@@ -52,6 +52,11 @@ SIGNATURES = {
     "ccal_exp_normalise_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ccal_isotonic_fit_binary": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, POINTER(c_int64), c_void_p]),
     "ccal_isotonic_transform": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_double, c_void_p, c_void_p]),
+    "ccal_ova_hist_fit": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "ccal_ova_apply": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_int, c_void_p, c_void_p]),
+    "ccal_sort_pairs_f64_u8": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "ccal_prefix_sum_i32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "ccal_kde2_pdf": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p,
                               c_void_p]),
     "ccal_density_ratio_apply": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_double, c_void_p,

@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libccal.so")
 STAMP = os.path.join(HERE, ".libccal.stamp")
 
 SOURCES = ["ccal_api.cu", "bin_stats.cu", "logits_ops.cu", "knn_dac.cu", "knn_tc.cu", "score_fused.cu", "density_ratio.cu", "isotonic.cu"]
-HEADERS = ["ccal_common.cuh", "sm100_ptx.cuh"]
+HEADERS = ["ccal_common.cuh", "sm100_ptx.cuh", "sort_scan.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

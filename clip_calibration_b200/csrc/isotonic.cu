@@ -4,7 +4,7 @@
 //
 //   exp_normalise_rows   p = exp(v) / sum(exp(v)) per row in float64, no max shift - the reference's own formula
 //                        (multi_isotonic_regression.py:26, :33) - and the flattened one-hot targets.
-//   isotonic_fit_binary  scikit-learn's `_build_y` for 0/1 targets: sort by x (cub radix sort), merge equal x
+//   isotonic_fit_binary  scikit-learn's `_build_y` for 0/1 targets: sort by x (radix sort, sort_scan.cuh), merge equal x
 //                        (`_make_unique`: a new value starts where x - first x of the current value >= 1e-15), pool adjacent violators,
 //                        drop interior points of constant stretches -> knots (X_thresholds_, y_thresholds_).
 //   isotonic_transform   clip to [X_min_, X_max_], linear interpolation between knots (scipy interp1d), plus the
@@ -16,8 +16,7 @@
 // are 0/1, so a block is the integer pair (ones, count): comparisons are exact cross-multiplications and the fitted
 // value is one correctly rounded division - there is no summation order to worry about.
 #include "ccal_common.cuh"
-
-#include <cub/cub.cuh>
+#include "sort_scan.cuh"
 
 #include <algorithm>
 #include <math_constants.h>
@@ -182,6 +181,21 @@ __global__ void iso_keep_kernel(const double* __restrict__ fy, int n_groups, uns
 // ---------------------------------------------------------------------------------------- transform
 constexpr int kIsoSmemKnots = 3072;           // knots staged in shared memory (48 KB); more stay in global memory / L1
 
+// scikit-learn IsotonicRegression.transform: out_of_bounds='clip', then scipy interp1d(kind='linear') on the knots
+__device__ __forceinline__ double iso_eval(const double* __restrict__ kx, const double* __restrict__ ky, int nk, double v) {
+  if (nk == 1) return ky[0];
+  const double x = fmin(fmax(v, kx[0]), kx[nk - 1]);
+  int lo = 0, hi = nk;                                         // searchsorted(kx, x, side='left')
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (kx[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  const int idx = min(max(lo, 1), nk - 1);
+  const double x0 = kx[idx - 1], x1 = kx[idx], y0 = ky[idx - 1], y1 = ky[idx];
+  const double slope = (y1 - y0) / (x1 - x0);
+  return slope * (x - x0) + y0;
+}
+
 template <bool kSmem>
 __global__ void __launch_bounds__(kIsoThreads)
 iso_transform_kernel(const double* __restrict__ gx, const double* __restrict__ gy, int nk, const double* __restrict__ t,
@@ -195,25 +209,7 @@ iso_transform_kernel(const double* __restrict__ gx, const double* __restrict__ g
     kx = s_knots;
     ky = s_knots + nk;
   }
-  const double x_min = kx[0], x_max = kx[nk - 1];
-  auto f = [&](double v) {
-    double r;
-    if (nk == 1) {
-      r = ky[0];
-    } else {
-      const double x = fmin(fmax(v, x_min), x_max);               // out_of_bounds='clip'
-      int lo = 0, hi = nk;                                         // searchsorted(kx, x, side='left')
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (kx[mid] < x) lo = mid + 1; else hi = mid;
-      }
-      const int idx = min(max(lo, 1), nk - 1);
-      const double x0 = kx[idx - 1], x1 = kx[idx], y0 = ky[idx - 1], y1 = ky[idx];
-      const double slope = (y1 - y0) / (x1 - x0);
-      r = slope * (x - x0) + y0;                                   // scipy interp1d, kind='linear'
-    }
-    return r + residual_scale * v;
-  };
+  auto f = [&](double v) { return iso_eval(kx, ky, nk, v) + residual_scale * v; };
   // four independent loads in flight per thread
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
@@ -227,6 +223,88 @@ iso_transform_kernel(const double* __restrict__ gx, const double* __restrict__ g
 }
 
 struct HostPair { int any_violation; int last_bid; };
+
+// ---------------------------------------------------------------------------------------- one-vs-all calibrators
+// netcal's multi-class scheme (AbstractCalibration._create_one_vs_all_models / _calibrate_multiclass): class j gets its
+// own BINARY calibrator fitted on (X[:, j], y == j); transform applies calibrator j to column j and divides every row
+// by its sum.  The matrix is row-major, so one warp walks a row with consecutive lanes on consecutive classes.
+constexpr int kOvaMaxBins = 64;
+
+__device__ __forceinline__ int ova_bin(double x, const double* edges, int n_bins) {
+  // np.linspace edges; bin i <=> edges[i] <= x < edges[i+1], the last bin closed on the right (scipy
+  // binned_statistic_dd / np.digitize - 1 clipped), values below edges[0] fall into bin 0
+  int b = 0;
+  for (int j = 1; j < n_bins; ++j) b += (x >= edges[j]) ? 1 : 0;
+  return b;
+}
+
+// counts / hits [c_tile][n_bins] live in shared memory for a tile of classes; grid = (row groups, class tiles)
+template <typename T>
+__global__ void __launch_bounds__(256)
+ova_hist_fit_kernel(const T* __restrict__ p, long long n, int c, const long long* __restrict__ labels,
+                    const double* __restrict__ edges_g, int n_bins, int tile_c, unsigned* __restrict__ count,
+                    unsigned* __restrict__ hits) {
+  extern __shared__ unsigned s_ova[];               // [tile_c * n_bins] counts, then [tile_c * n_bins] hits
+  __shared__ double s_edges[kOvaMaxBins + 1];
+  const int c0 = blockIdx.y * tile_c;
+  const int cw = min(tile_c, c - c0);
+  const int cells = cw * n_bins;
+  for (int j = threadIdx.x; j < 2 * cells; j += 256) s_ova[j] = 0;
+  if (threadIdx.x <= n_bins) s_edges[threadIdx.x] = edges_g[threadIdx.x];
+  __syncthreads();
+  unsigned* s_cnt = s_ova;
+  unsigned* s_hit = s_ova + cells;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < n; row += (long long)gridDim.x * 8) {
+    const T* x = p + row * (long long)c + c0;
+    const long long lab = labels[row] - c0;
+    for (int j = lane; j < cw; j += 32) {
+      const int b = ova_bin((double)x[j], s_edges, n_bins);
+      atomicAdd(&s_cnt[j * n_bins + b], 1u);
+      if (j == lab) atomicAdd(&s_hit[j * n_bins + b], 1u);
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < cells; j += 256) {
+    if (s_cnt[j]) atomicAdd(&count[(long long)c0 * n_bins + j], s_cnt[j]);
+    if (s_hit[j]) atomicAdd(&hits[(long long)c0 * n_bins + j], s_hit[j]);
+  }
+}
+
+// kMode 0: histogram binning (out = bin_map[class][bin]); 1: isotonic (out = f_class(x), knots of class j are
+// knots[off[j] .. off[j+1]), a class without knots gives 0).  One warp per row; the row sum is accumulated in class
+// order per lane and combined by a fixed butterfly, so the result does not depend on the launch shape.
+template <typename T, int kMode>
+__global__ void __launch_bounds__(256)
+ova_apply_kernel(const T* __restrict__ p, long long n, int c, const double* __restrict__ edges_g, int n_bins,
+                 const double* __restrict__ bin_map, const double* __restrict__ kx, const double* __restrict__ ky,
+                 const int* __restrict__ off, int normalise, double* __restrict__ out) {
+  __shared__ double s_edges[kOvaMaxBins + 1];
+  if (kMode == 0 && threadIdx.x <= n_bins) s_edges[threadIdx.x] = edges_g[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < n; row += (long long)gridDim.x * 8) {
+    const T* x = p + row * (long long)c;
+    double* o = out + row * (long long)c;
+    double sum = 0.0;
+    for (int j = lane; j < c; j += 32) {
+      const double v = (double)x[j];
+      double r;
+      if (kMode == 0) {
+        r = bin_map[(long long)j * n_bins + ova_bin(v, s_edges, n_bins)];
+      } else {
+        const int a = off[j], nk = off[j + 1] - a;
+        r = nk > 0 ? iso_eval(kx + a, ky + a, nk, v) : 0.0;
+      }
+      o[j] = r;
+      sum += r;
+    }
+    if (!normalise) continue;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+    for (int j = lane; j < c; j += 32) o[j] = o[j] / sum;      // every lane re-reads only what it wrote itself
+  }
+}
 
 }  // namespace ccal
 
@@ -261,20 +339,14 @@ extern "C" int ccal_isotonic_fit_binary(const double* x, const unsigned char* y,
   cudaStream_t stream = (cudaStream_t)stream_;
   CCAL_REQUIRE(n >= 1 && n < 2147483647ll, "ccal_isotonic_fit_binary: n must be in [1, 2^31) (got %lld)", (long long)n);
   CCAL_REQUIRE(x && y && knots_x && knots_y && n_knots_host, "ccal_isotonic_fit_binary: NULL pointer");
-  const int ni = (int)n;
 
   // ---- workspace layout
-  size_t sort_bytes = 0, scan_bytes = 0, select_bytes = 0;
-  CCAL_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const double*)nullptr, (double*)nullptr,
-                                               (const unsigned char*)nullptr, (unsigned char*)nullptr, ni, 0, 64, stream));
-  CCAL_CUDA_OK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, ni, stream));
-  CCAL_CUDA_OK(cub::DeviceSelect::Flagged(nullptr, select_bytes, (const double*)nullptr, (const unsigned char*)nullptr,
-                                          (double*)nullptr, (int*)nullptr, ni, stream));
-  const size_t temp_bytes = std::max(sort_bytes, std::max(scan_bytes, select_bytes));
+  const SortPlan plan = sort_plan(n);
+  const size_t scan_bytes = scan_workspace_bytes(n);
   auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t sz_d = up(sizeof(double) * n), sz_u8 = up(n), sz_i = up(sizeof(int) * n), sz_u64 = up(8 * (size_t)n);
-  // xs, ux, fy | ys, keep | flag, gid, start0, start1 | ones0, cnt0, ones1, cnt1 | small | cub temp
-  const size_t total = 3 * sz_d + 2 * sz_u8 + 4 * sz_i + 4 * sz_u64 + 256 + up(temp_bytes);
+  // xs, ux, fy | ys, keep | flag, gid, start0, start1 | ones0, cnt0, ones1, cnt1 | small | prefix-sum tile sums | sort scratch
+  const size_t total = 3 * sz_d + 2 * sz_u8 + 4 * sz_i + 4 * sz_u64 + 256 + up(scan_bytes) + up(plan.total);
   AsyncWorkspace ws;
   CCAL_CUDA_OK(ws.alloc(total, stream));
   unsigned char* p = ws.ptr;
@@ -286,13 +358,12 @@ extern "C" int ccal_isotonic_fit_binary(const double* x, const unsigned char* y,
   unsigned long long* ones[2]; unsigned long long* cnt[2];
   ones[0] = (unsigned long long*)take(sz_u64); cnt[0] = (unsigned long long*)take(sz_u64);
   ones[1] = (unsigned long long*)take(sz_u64); cnt[1] = (unsigned long long*)take(sz_u64);
-  int* small = (int*)take(256);                 // [0] any_violation, [1] number selected
-  void* temp = take(up(temp_bytes));
+  int* small = (int*)take(256);                 // [0] any_violation
+  void* scan_ws = take(up(scan_bytes));
+  unsigned char* sort_ws = take(up(plan.total));
 
   // ---- sort by x, merge equal x into groups (ones, count)
-  size_t tb = temp_bytes;
-  CCAL_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, tb, x, xs, y, ys, ni, 0, 64, stream));
-  note_launch();
+  CCAL_CUDA_OK(sort_pairs_f64_u8(x, y, n, xs, ys, sort_ws, stream));
   iso_unique_flags_kernel<<<iso_grid(n), kIsoThreads, 0, stream>>>(xs, n, flag);
   note_launch();
   // anchored starts inside runs of close neighbours (buffers: gid = second flag array, start[] = jump tables)
@@ -315,9 +386,7 @@ extern "C" int ccal_isotonic_fit_binary(const double* x, const unsigned char* y,
     }
     if (f_cur != flag) CCAL_CUDA_OK(cudaMemcpyAsync(flag, f_cur, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
   }
-  tb = temp_bytes;
-  CCAL_CUDA_OK(cub::DeviceScan::InclusiveSum(temp, tb, flag, gid, ni, stream));
-  note_launch();
+  CCAL_CUDA_OK(prefix_sum_i32(flag, gid, n, true, scan_ws, stream));
   CCAL_CUDA_OK(cudaMemsetAsync(ones[0], 0, 8 * (size_t)n, stream));
   CCAL_CUDA_OK(cudaMemsetAsync(cnt[0], 0, 8 * (size_t)n, stream));
   iso_group_kernel<<<iso_grid(n), kIsoThreads, 0, stream>>>(xs, ys, flag, gid, n, ux, ones[0], cnt[0], start[0]);
@@ -335,9 +404,7 @@ extern "C" int ccal_isotonic_fit_binary(const double* x, const unsigned char* y,
     CCAL_CUDA_OK(cudaMemsetAsync(small, 0, sizeof(int), stream));
     iso_heads_kernel<<<(nb + kIsoThreads - 1) / kIsoThreads, kIsoThreads, 0, stream>>>(ones[cur], cnt[cur], nb, head, small);
     note_launch();
-    tb = temp_bytes;
-    CCAL_CUDA_OK(cub::DeviceScan::InclusiveSum(temp, tb, head, bid, nb, stream));
-    note_launch();
+    CCAL_CUDA_OK(prefix_sum_i32(head, bid, nb, true, scan_ws, stream));
     HostPair hp;
     CCAL_CUDA_OK(cudaMemcpyAsync(&hp.any_violation, small, sizeof(int), cudaMemcpyDeviceToHost, stream));
     CCAL_CUDA_OK(cudaMemcpyAsync(&hp.last_bid, bid + (nb - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -359,14 +426,15 @@ extern "C" int ccal_isotonic_fit_binary(const double* x, const unsigned char* y,
   note_launch();
   iso_keep_kernel<<<(n_groups + kIsoThreads - 1) / kIsoThreads, kIsoThreads, 0, stream>>>(fy, n_groups, keep);
   note_launch();
-  tb = temp_bytes;
-  CCAL_CUDA_OK(cub::DeviceSelect::Flagged(temp, tb, ux, keep, knots_x, small + 1, n_groups, stream));
+  // compaction: slot of a kept point = number of kept points up to and including it (flag / gid are free again)
+  const unsigned kb = (n_groups + kIsoThreads - 1) / kIsoThreads;
+  compact_flags_kernel<<<kb, kIsoThreads, 0, stream>>>(keep, n_groups, flag);
   note_launch();
-  tb = temp_bytes;
-  CCAL_CUDA_OK(cub::DeviceSelect::Flagged(temp, tb, fy, keep, knots_y, small + 1, n_groups, stream));
+  CCAL_CUDA_OK(prefix_sum_i32(flag, gid, n_groups, true, scan_ws, stream));
+  compact_pair_kernel<<<kb, kIsoThreads, 0, stream>>>(ux, fy, keep, gid, n_groups, knots_x, knots_y);
   note_launch();
   int n_knots = 0;
-  CCAL_CUDA_OK(cudaMemcpyAsync(&n_knots, small + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CCAL_CUDA_OK(cudaMemcpyAsync(&n_knots, gid + (n_groups - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
   CCAL_CUDA_OK(cudaStreamSynchronize(stream));
   CCAL_CUDA_OK(cudaGetLastError());
   *n_knots_host = n_knots;
@@ -386,6 +454,84 @@ extern "C" int ccal_isotonic_transform(const double* knots_x, const double* knot
                                                                                          residual_scale, out);
   else
     iso_transform_kernel<false><<<(int)grid, kIsoThreads, 0, stream>>>(knots_x, knots_y, (int)n_knots, t, n, residual_scale, out);
+  note_launch();
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}
+
+// ---- the device primitives above, exported so that tests can drive them directly (tests/test_gpu_parity.py)
+extern "C" int ccal_sort_pairs_f64_u8(const double* keys, const unsigned char* vals, int64_t n, double* keys_out,
+                                      unsigned char* vals_out, ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE(n >= 0 && n < 2147483647ll, "ccal_sort_pairs_f64_u8: n must be in [0, 2^31) (got %lld)", (long long)n);
+  if (n == 0) return CCAL_OK;
+  CCAL_REQUIRE(keys && vals && keys_out && vals_out, "ccal_sort_pairs_f64_u8: NULL pointer");
+  CCAL_REQUIRE((const void*)keys != (const void*)keys_out && vals != vals_out, "ccal_sort_pairs_f64_u8: in-place sort is not supported");
+  AsyncWorkspace ws;
+  CCAL_CUDA_OK(ws.alloc(sort_plan(n).total, stream));
+  CCAL_CUDA_OK(sort_pairs_f64_u8(keys, vals, n, keys_out, vals_out, ws.ptr, stream));
+  return CCAL_OK;
+}
+
+extern "C" int ccal_prefix_sum_i32(const int* in, int* out, int64_t n, int inclusive, ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE(n >= 0, "ccal_prefix_sum_i32: negative n");
+  if (n == 0) return CCAL_OK;
+  CCAL_REQUIRE(in && out, "ccal_prefix_sum_i32: NULL pointer");
+  AsyncWorkspace ws;
+  CCAL_CUDA_OK(ws.alloc(scan_workspace_bytes(n), stream));
+  CCAL_CUDA_OK(prefix_sum_i32(in, out, n, inclusive != 0, ws.ptr, stream));
+  return CCAL_OK;
+}
+
+// ---- one-vs-all (netcal-style) calibrators
+extern "C" int ccal_ova_hist_fit(const float* p_f32, const double* p_f64, int64_t n, int c, const int64_t* labels,
+                                 const double* edges, int n_bins, uint32_t* count, uint32_t* hits, ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE((p_f32 != nullptr) != (p_f64 != nullptr), "ccal_ova_hist_fit: exactly one of p_f32 / p_f64 must be given");
+  CCAL_REQUIRE(n >= 0 && c >= 1, "ccal_ova_hist_fit: bad shape n=%lld c=%d", (long long)n, c);
+  CCAL_REQUIRE(n_bins >= 1 && n_bins <= kOvaMaxBins, "ccal_ova_hist_fit: n_bins must be in [1, %d] (got %d)", kOvaMaxBins, n_bins);
+  CCAL_REQUIRE(edges && count && hits && (labels || n == 0), "ccal_ova_hist_fit: NULL pointer");
+  CCAL_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(uint32_t) * (size_t)c * n_bins, stream));
+  CCAL_CUDA_OK(cudaMemsetAsync(hits, 0, sizeof(uint32_t) * (size_t)c * n_bins, stream));
+  if (n == 0) return CCAL_OK;
+  const int tile_c = std::min(c, 20480 / n_bins);              // 2 x tile_c x n_bins counters <= 160 KB of shared memory
+  const size_t smem = 2 * sizeof(unsigned) * (size_t)tile_c * n_bins;
+  const int tiles = (c + tile_c - 1) / tile_c;
+  const unsigned gx = (unsigned)std::min<long long>((n + 7) / 8, std::max(1, num_sms() * 2 / tiles));
+  const long long* lab = reinterpret_cast<const long long*>(labels);
+#define CCAL_LAUNCH_OVA_FIT(T, ptr)                                                                                   \
+  do {                                                                                                                \
+    CCAL_CUDA_OK(cudaFuncSetAttribute(ova_hist_fit_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    ova_hist_fit_kernel<T><<<dim3(gx, tiles), 256, smem, stream>>>(ptr, n, c, lab, edges, n_bins, tile_c, count, hits); \
+  } while (0)
+  if (p_f32) CCAL_LAUNCH_OVA_FIT(float, p_f32); else CCAL_LAUNCH_OVA_FIT(double, p_f64);
+#undef CCAL_LAUNCH_OVA_FIT
+  note_launch();
+  CCAL_CUDA_OK(cudaGetLastError());
+  return CCAL_OK;
+}
+
+extern "C" int ccal_ova_apply(const float* p_f32, const double* p_f64, int64_t n, int c, const double* edges, int n_bins,
+                              const double* bin_map, const double* knots_x, const double* knots_y, const int32_t* knot_off,
+                              int normalise, double* out, ccal_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CCAL_REQUIRE((p_f32 != nullptr) != (p_f64 != nullptr), "ccal_ova_apply: exactly one of p_f32 / p_f64 must be given");
+  CCAL_REQUIRE(n >= 0 && c >= 1, "ccal_ova_apply: bad shape n=%lld c=%d", (long long)n, c);
+  const bool hist = bin_map != nullptr;
+  CCAL_REQUIRE(hist != (knot_off != nullptr), "ccal_ova_apply: give either bin_map (+ edges) or the knots (+ knot_off)");
+  if (hist) CCAL_REQUIRE(edges && n_bins >= 1 && n_bins <= kOvaMaxBins, "ccal_ova_apply: edges / n_bins (1..%d) are required with bin_map", kOvaMaxBins);
+  else CCAL_REQUIRE(knots_x && knots_y, "ccal_ova_apply: knots_x / knots_y are required with knot_off");
+  if (n == 0) return CCAL_OK;
+  CCAL_REQUIRE(out != nullptr, "ccal_ova_apply: out is NULL");
+  const unsigned gx = (unsigned)std::min<long long>((n + 7) / 8, (long long)num_sms() * 8);
+#define CCAL_LAUNCH_OVA_APPLY(T, ptr)                                                                                  \
+  do {                                                                                                                 \
+    if (hist) ova_apply_kernel<T, 0><<<gx, 256, 0, stream>>>(ptr, n, c, edges, n_bins, bin_map, nullptr, nullptr, nullptr, normalise, out); \
+    else ova_apply_kernel<T, 1><<<gx, 256, 0, stream>>>(ptr, n, c, nullptr, 0, nullptr, knots_x, knots_y, knot_off, normalise, out);        \
+  } while (0)
+  if (p_f32) CCAL_LAUNCH_OVA_APPLY(float, p_f32); else CCAL_LAUNCH_OVA_APPLY(double, p_f64);
+#undef CCAL_LAUNCH_OVA_APPLY
   note_launch();
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;

@@ -489,6 +489,84 @@ def isotonic_transform(knots_x: torch.Tensor, knots_y: torch.Tensor, t: torch.Te
     return out
 
 
+def ova_hist_fit(probs: torch.Tensor, labels: torch.Tensor, edges: torch.Tensor):
+    """Per class j and bin b of `edges` (float64 [n_bins + 1] CUDA): how many rows have probs[i, j] in the bin, and how
+    many of those carry the label j -> (count, hits) uint32-valued int64 CUDA tensors [C, n_bins]."""
+    lib = _lib.load()
+    probs = _need_cuda("probs", probs, (torch.float32, torch.float64), 2)
+    n, c = probs.shape
+    labels = _need_cuda("labels", labels, torch.int64, 1)
+    edges = _need_cuda("edges", edges, torch.float64, 1)
+    if labels.shape[0] != n:
+        raise ValueError("ova_hist_fit: one label per row is required")
+    n_bins = edges.numel() - 1
+    both = torch.empty((2, c, n_bins), dtype=torch.int32, device=probs.device)
+    f32 = probs.dtype == torch.float32
+    with torch.cuda.device(probs.device):
+        rc = lib.ccal_ova_hist_fit(_ptr(probs) if f32 else None, None if f32 else _ptr(probs), n, c, _ptr(labels),
+                                   _ptr(edges), n_bins, _ptr(both[0]), _ptr(both[1]), _stream())
+    _lib.check(rc, "ccal_ova_hist_fit")
+    both = both.to(torch.int64) & 0xFFFFFFFF
+    return both[0], both[1]
+
+
+def ova_apply(probs: torch.Tensor, *, edges: Optional[torch.Tensor] = None, bin_map: Optional[torch.Tensor] = None,
+              knots_x: Optional[torch.Tensor] = None, knots_y: Optional[torch.Tensor] = None,
+              knot_off: Optional[torch.Tensor] = None, normalise: bool = True) -> torch.Tensor:
+    """Column j of probs [N, C] through class j's binary calibrator - a bin map (edges + bin_map [C, n_bins]) or an
+    isotonic function (concatenated knots + knot_off [C + 1] int32) - then each row divided by its sum; float64."""
+    lib = _lib.load()
+    probs = _need_cuda("probs", probs, (torch.float32, torch.float64), 2)
+    n, c = probs.shape
+    out = torch.empty((n, c), dtype=torch.float64, device=probs.device)
+    n_bins = 0
+    if bin_map is not None:
+        edges = _need_cuda("edges", edges, torch.float64, 1)
+        bin_map = _need_cuda("bin_map", bin_map, torch.float64, 2)
+        n_bins = edges.numel() - 1
+        if tuple(bin_map.shape) != (c, n_bins):
+            raise ValueError("ova_apply: bin_map must be [C, n_bins]")
+    else:
+        knots_x = _need_cuda("knots_x", knots_x, torch.float64, 1)
+        knots_y = _need_cuda("knots_y", knots_y, torch.float64, 1)
+        knot_off = _need_cuda("knot_off", knot_off, torch.int32, 1)
+        if knot_off.numel() != c + 1 or knots_x.shape != knots_y.shape:
+            raise ValueError("ova_apply: knot_off must hold C + 1 offsets into equally long knots_x / knots_y")
+    f32 = probs.dtype == torch.float32
+    with torch.cuda.device(probs.device):
+        rc = lib.ccal_ova_apply(_ptr(probs) if f32 else None, None if f32 else _ptr(probs), n, c, _ptr(edges), n_bins,
+                                _ptr(bin_map), _ptr(knots_x), _ptr(knots_y), _ptr(knot_off), int(bool(normalise)),
+                                _ptr(out), _stream())
+    _lib.check(rc, "ccal_ova_apply")
+    return out
+
+
+def sort_pairs_f64_u8(keys: torch.Tensor, vals: torch.Tensor):
+    """Stable ascending sort of (float64 key, uint8 payload) pairs by the library's own radix sort (the sort of the
+    isotonic fit).  Synchronises."""
+    lib = _lib.load()
+    keys = _need_cuda("keys", keys.reshape(-1), torch.float64, 1)
+    vals = _need_cuda("vals", vals.reshape(-1), torch.uint8, 1)
+    if keys.shape != vals.shape:
+        raise ValueError("sort_pairs_f64_u8: one payload byte per key is required")
+    ko, vo = torch.empty_like(keys), torch.empty_like(vals)
+    with torch.cuda.device(keys.device):
+        rc = lib.ccal_sort_pairs_f64_u8(_ptr(keys), _ptr(vals), keys.numel(), _ptr(ko), _ptr(vo), _stream())
+    _lib.check(rc, "ccal_sort_pairs_f64_u8")
+    return ko, vo
+
+
+def prefix_sum_i32(x: torch.Tensor, inclusive: bool = True) -> torch.Tensor:
+    """int32 prefix sum of a flat CUDA tensor by the library's own scan kernels."""
+    lib = _lib.load()
+    x = _need_cuda("x", x.reshape(-1), torch.int32, 1)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = lib.ccal_prefix_sum_i32(_ptr(x), _ptr(out), x.numel(), int(bool(inclusive)), _stream())
+    _lib.check(rc, "ccal_prefix_sum_i32")
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # K3  bin statistics and exact order statistics
 # --------------------------------------------------------------------------------------

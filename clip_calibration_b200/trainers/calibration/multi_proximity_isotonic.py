@@ -3,10 +3,10 @@ proximity-binned wrapper `VLCalibration` builds for the bin-based calibrators (v
 grouped by proximity quantile (or uniform) bins and every group gets its own calibrator.
 
 Provided: `method_name='multi_isotonic_regression'` with `MultiIsotonicRegression` (the scikit-learn based calibrator;
-GPU fit, see multi_isotonic_regression.py), `bin_strategy` 'quantile' (np.percentile edges from exact device order
-statistics) and 'uniform'.  Not provided: the netcal methods ('histogram_binning', 'isotonic_regression' - netcal is not
-installed and unpinned, nothing could pin a restatement), 'kmeans' bins, and `MultiProximityIsotonicRegression`, which
-nothing in the reference calls.
+GPU fit, see multi_isotonic_regression.py), 'histogram_binning' / 'isotonic_regression' with the one-vs-all calibrators
+of netcal_binning.py (netcal's published scheme; parity with netcal itself unpinned - it is not installed), `bin_strategy`
+'quantile' (np.percentile edges from exact device order statistics) and 'uniform'.  Not provided: 'kmeans' bins, and
+`MultiProximityIsotonicRegression`, which nothing in the reference calls.
 """
 from __future__ import annotations
 
@@ -21,9 +21,9 @@ from .multi_isotonic_regression import MultiIsotonicRegression, _device_matrix
 class BinMeanShift():
 
     def __init__(self, method_name, method, bin_strategy='quantile', normalize_conf=False, proximity_bin=10, **kwargs) -> None:
-        if method_name != 'multi_isotonic_regression':
-            raise NotImplementedError(f"BinMeanShift method {method_name!r}: only 'multi_isotonic_regression' is provided "
-                                      "(the netcal calibrators are outside the accelerated path)")
+        if method_name not in ('multi_isotonic_regression', 'histogram_binning', 'isotonic_regression'):
+            raise NotImplementedError(f"BinMeanShift method {method_name!r}: 'multi_isotonic_regression', "
+                                      "'histogram_binning' and 'isotonic_regression' are provided")
         if bin_strategy not in ('quantile', 'uniform'):
             raise NotImplementedError(f"bin_strategy {bin_strategy!r}: only 'quantile' and 'uniform' are provided")
         self.method_name = method_name
@@ -77,6 +77,9 @@ class BinMeanShift():
     def _apply(self, logit, proximity, label):
         as_numpy = not isinstance(logit, torch.Tensor)
         x = _device_matrix(logit)
+        if self.method_name in ('histogram_binning', 'isotonic_regression'):
+            # logit = np.exp(logit) / np.sum(np.exp(logit), 1)[:, None]   (reference :219-220, :241-242)
+            x, _ = native.exp_normalise_rows(x)
         bin_no = self._bin_numbers(proximity)
         if bin_no.numel() != x.shape[0]:
             raise ValueError("one proximity value per row is required")

@@ -3,10 +3,10 @@
 
 In scope: DAC (dac_flag) followed by softmax; the `scaling_based` base calibrator with `procal_flag` =
 DensityRatioCalibration (reference :116-119, :95-96; CUDA KDE, density_ratio_calibration.py); the `bin_based`
-base calibrator 'multi_isotonic_regression', plain or proximity-binned through BinMeanShift (reference :133-134,
-:146-148, :97-102; GPU isotonic fit, multi_isotonic_regression.py / multi_proximity_isotonic.py).  The two netcal
-calibrators ('histogram_binning', 'isotonic_regression'; netcal is unpinned and not installed) are out of scope:
-requesting one raises NotImplementedError instead of silently skipping it.
+base calibrators 'multi_isotonic_regression', 'histogram_binning' and 'isotonic_regression', plain or
+proximity-binned through BinMeanShift (reference :121-148, :97-102; GPU isotonic fit, multi_isotonic_regression.py /
+multi_proximity_isotonic.py; the latter two are netcal's one-vs-all calibrators restated in netcal_binning.py -
+netcal is an unpinned pip dependency that is not installed, so parity with netcal itself is unpinned).
 
 `predict(logits, proximity)` keeps the reference contract and returns probabilities [N, C].
 `predict_confidence` / `predict_from_features` are the additive routes that return only
@@ -22,6 +22,14 @@ from .density_ratio_calibration import DensityRatioCalibration
 from .distanse_aware_calibration import DistanseAwareCalibration
 from .multi_isotonic_regression import MultiIsotonicRegression
 from .multi_proximity_isotonic import BinMeanShift
+from .netcal_binning import HistogramBinning, IsotonicRegression
+
+# name -> (class, constructor kwargs): reference :125-148
+_BIN_CALIBRATORS = {
+    "histogram_binning": (HistogramBinning, {"bins": 10}),
+    "isotonic_regression": (IsotonicRegression, {}),
+    "multi_isotonic_regression": (MultiIsotonicRegression, {}),
+}
 
 
 class VLCalibration():
@@ -57,20 +65,22 @@ class VLCalibration():
         """reference :112-150, `scaling_based` branch: the density-ratio calibrator is fitted on the validation
         (calibration) set - softmax of the un-scaled validation logits (:59-60), their argmax, labels, proximity."""
         if self.base_calibration_mode == "bin_based":
-            if base_bin_calibrator_name != "multi_isotonic_regression":
-                raise NotImplementedError(
-                    f"bin calibrator {base_bin_calibrator_name!r}: the netcal calibrators (histogram_binning, "
-                    "isotonic_regression) are outside the accelerated path; use the reference's VLCalibration for them")
+            if base_bin_calibrator_name not in _BIN_CALIBRATORS:
+                return None                         # the reference's if/elif chain builds nothing for other names
+            method, kwargs = _BIN_CALIBRATORS[base_bin_calibrator_name]
             val_probs, _, _ = self._val_probs()
             labels = self._val_labels()
             if self.procal_flag:
                 self._need_proximity(val_image_proximity, "bin_based calibration with procal_flag")
-                base_calibrator = BinMeanShift("multi_isotonic_regression", MultiIsotonicRegression,
-                                               bin_strategy="quantile", normalize_conf=False, proximity_bin=5)
+                base_calibrator = BinMeanShift(base_bin_calibrator_name, method, bin_strategy="quantile",
+                                               normalize_conf=False, proximity_bin=5, **kwargs)
                 base_calibrator.fit_transform(val_probs, val_image_proximity, labels)
-            else:
-                base_calibrator = MultiIsotonicRegression()
+            elif base_bin_calibrator_name == "multi_isotonic_regression":
+                base_calibrator = method()
                 base_calibrator.fit_transform(val_probs, labels)
+            else:
+                base_calibrator = method(**kwargs)
+                base_calibrator.fit(val_probs, labels)
             return base_calibrator
         if not (self.base_calibration_mode == "scaling_based" and self.procal_flag):
             return None                             # the reference builds nothing in this case either

@@ -258,6 +258,37 @@ CCAL_API int ccal_isotonic_fit_binary(const double* x, const unsigned char* y, i
 CCAL_API int ccal_isotonic_transform(const double* knots_x, const double* knots_y, int64_t n_knots, const double* t,
                             int64_t n, double residual_scale, double* out, ccal_stream_t stream);
 
+/* ---- one-vs-all bin-based calibrators (netcal.binning.HistogramBinning / IsotonicRegression) -----------------
+ * Reference call sites: trainers/calibration/vl_calibrator.py:20-21, :125-131 (under BinMeanShift), :137-143 (plain).
+ * netcal itself is a pip dependency (requirements.txt:6, unpinned, not vendored): the kernels follow netcal 1.3's
+ * published multi-class scheme - class j gets a BINARY calibrator fitted on (X[:, j], y == j); transform applies
+ * calibrator j to column j and divides each row by its sum (AbstractCalibration._create_one_vs_all_models /
+ * _calibrate_multiclass).  Parity with netcal is unpinned; the scikit-learn isotonic fit inside is pinned.
+ * ccal_ova_hist_fit: count[j, b] / hits[j, b] (uint32 [c, n_bins], zeroed here) = number of rows whose p[i, j] falls
+ *   into bin b of `edges` (n_bins + 1 float64 values: edges[b] <= x < edges[b+1], last bin closed) / those with
+ *   labels[i] == j.  p is fp32 or fp64 (exactly one pointer non-NULL), n_bins <= 64.
+ * ccal_ova_apply: out[i, j] = bin_map[j, bin(p[i, j])] (bin_map float64 [c, n_bins] given) or the isotonic function of
+ *   class j at p[i, j] (knot_off int32 [c + 1] given: knots of class j are knots_x/knots_y[knot_off[j] .. knot_off[j+1]),
+ *   clip + linear interpolation as ccal_isotonic_transform; a class without knots gives 0); normalise != 0 divides each
+ *   row by its sum.
+ */
+CCAL_API int ccal_ova_hist_fit(const float* p_f32, const double* p_f64, int64_t n, int c, const int64_t* labels,
+                      const double* edges, int n_bins, uint32_t* count, uint32_t* hits, ccal_stream_t stream);
+CCAL_API int ccal_ova_apply(const float* p_f32, const double* p_f64, int64_t n, int c, const double* edges, int n_bins,
+                   const double* bin_map, const double* knots_x, const double* knots_y, const int32_t* knot_off,
+                   int normalise, double* out, ccal_stream_t stream);
+
+/* ---- device primitives of the bin-based calibrators (csrc/sort_scan.cuh), exported for tests ------------------
+ * The isotonic fit (sklearn/isotonic.py: `order = np.lexsort((y, X))`, `_make_unique`, trim_duplicates) needs a stable
+ * sort by x, prefix sums and a flagged compaction; these are the library's own kernels, not a vendor library's.
+ * ccal_sort_pairs_f64_u8: stable ascending sort of (keys[i], vals[i]), n < 2^31, not in place; -0.0 < +0.0.
+ *   SYNCHRONISES the stream (which of the 8 digit passes run is decided on the host).
+ * ccal_prefix_sum_i32: out[i] = in[0] + ... + in[i] (inclusive != 0) or ... + in[i-1]; out may be in; sums must fit int32.
+ */
+CCAL_API int ccal_sort_pairs_f64_u8(const double* keys, const unsigned char* vals, int64_t n, double* keys_out,
+                           unsigned char* vals_out, ccal_stream_t stream);
+CCAL_API int ccal_prefix_sum_i32(const int* in, int* out, int64_t n, int inclusive, ccal_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

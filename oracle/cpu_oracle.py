@@ -17,6 +17,9 @@ semantics are not in the reference tree); ts_loss_and_grad is pinned to torch au
 density_ratio_fit / density_ratio_predict: the reference's own arithmetic is pinned by running the real
 DensityRatioCalibration class over KDEMultivariateCC; the KDE itself restates statsmodels (absent here,
 unpinned in the reference's requirements.txt) -> that part is parity UNPINNED, cross-checked against sklearn.
+NetcalHistogramBinningCC / NetcalIsotonicRegressionCC: netcal (requirements.txt:6, unpinned, absent here) restated from
+netcal 1.3's published one-vs-all scheme -> parity with netcal UNPINNED; the reference's own BinMeanShift is run
+unmodified over these classes by make_golden.py, which pins the reference-side arithmetic around them.
 """
 from __future__ import annotations
 
@@ -409,3 +412,87 @@ def bin_mean_shift_transform(state, logit, proximity):
         if len(idx):
             out[idx] = multi_isotonic_transform(cals[b], logit[idx])
     return out
+
+
+class _NetcalOneVsAllCC:
+    """netcal.AbstractCalibration for multi-class input, `detection=False` (published algorithm of netcal 1.3:
+    `_create_one_vs_all_models` + `_calibrate_multiclass`): a binary sub-model per class that occurs in y, fitted on
+    (X[:, j], y == j); transform puts sub-model j's output into column j (classes without a sub-model stay 0) and
+    divides each row by its sum unless `independent_probabilities`.  A 1-D X is the binary problem itself.  netcal is
+    called by the reference at trainers/calibration/vl_calibrator.py:125-131, :137-143 and
+    multi_proximity_isotonic.py:219-221, :241-243.  PARITY WITH NETCAL UNPINNED (not installed)."""
+
+    def __init__(self, independent_probabilities=False):
+        self.independent_probabilities = independent_probabilities
+        self.models = None
+        self.binary = False
+
+    def fit(self, X, y):
+        X = np.asarray(X, dtype=np.float64)
+        y = np.asarray(y)
+        if y.ndim == 2:
+            y = np.argmax(y, axis=1)
+        self.binary = X.ndim == 1
+        if self.binary:
+            self.models = [self._fit_binary(X, (y == 1).astype(np.float64))]
+            return self
+        self.models = []
+        for j in range(X.shape[1]):
+            hit = y == j
+            self.models.append(self._fit_binary(X[:, j], hit.astype(np.float64)) if hit.any() else None)
+        return self
+
+    def transform(self, X):
+        X = np.asarray(X, dtype=np.float64)
+        if self.binary:
+            return self._apply_binary(self.models[0], X)
+        out = np.zeros(X.shape, np.float64)
+        for j, m in enumerate(self.models):
+            if m is not None:
+                out[:, j] = self._apply_binary(m, X[:, j])
+        if not self.independent_probabilities:
+            with np.errstate(invalid="ignore", divide="ignore"):
+                out = out / np.sum(out, axis=1, keepdims=True)
+        return out
+
+    def fit_transform(self, X, y):
+        return self.fit(X, y).transform(X)
+
+
+class NetcalHistogramBinningCC(_NetcalOneVsAllCC):
+    """netcal.binning.HistogramBinning(bins, equal_intervals=True): bin bounds np.linspace(0, 1, bins + 1), bin map =
+    scipy.stats.binned_statistic_dd(X, y, 'mean') (last bin closed), empty bins filled with the bin centre; transform
+    looks the bin up with np.digitize - 1 clipped to the valid range."""
+
+    def __init__(self, bins=10, equal_intervals=True, detection=False, independent_probabilities=False):
+        super().__init__(independent_probabilities)
+        assert equal_intervals and not detection
+        self.bins = bins
+
+    def _fit_binary(self, x, y):
+        from scipy.stats import binned_statistic_dd
+        edges = np.linspace(0.0, 1.0, self.bins + 1)
+        mean, _, _ = binned_statistic_dd(x.reshape(-1, 1), y, statistic="mean", bins=[edges])
+        centres = (edges[1:] + edges[:-1]) * 0.5
+        return edges, np.where(np.isnan(mean), centres, mean)
+
+    def _apply_binary(self, model, x):
+        edges, bin_map = model
+        idx = np.clip(np.digitize(x, edges) - 1, 0, self.bins - 1)
+        return bin_map[idx]
+
+
+class NetcalIsotonicRegressionCC(_NetcalOneVsAllCC):
+    """netcal.binning.IsotonicRegression: sklearn.isotonic.IsotonicRegression(increasing=True, out_of_bounds='clip')
+    per binary problem."""
+
+    def __init__(self, detection=False, independent_probabilities=False):
+        super().__init__(independent_probabilities)
+        assert not detection
+
+    def _fit_binary(self, x, y):
+        from sklearn.isotonic import IsotonicRegression
+        return IsotonicRegression(increasing=True, out_of_bounds="clip").fit(x, y)
+
+    def _apply_binary(self, model, x):
+        return model.transform(x)

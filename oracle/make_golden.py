@@ -255,6 +255,34 @@ def isotonic():
     np.savez_compressed(os.path.join(OUT, "isotonic.npz"), **out)
 
 
+def netcal_binning():
+    """The two netcal calibrators `VLCalibration` can build (vl_calibrator.py:125-131 under BinMeanShift, :137-143
+    plain).  netcal is not installed: the oracle's restatement of its published one-vs-all scheme stands in for
+    `netcal.binning.{HistogramBinning, IsotonicRegression}` (PARITY WITH NETCAL UNPINNED) while the reference's own
+    BinMeanShift (multi_proximity_isotonic.py:130-247: exp-normalisation of its input for these two methods, proximity
+    bins, per-bin fit_transform / transform, re-ordering) runs unmodified around it."""
+    from trainers.calibration.multi_proximity_isotonic import BinMeanShift
+    g = np.load(os.path.join(OUT, "density_ratio.npz"))
+    vp, tp = g["val_probs"].astype(np.float64), g["test_probs"].astype(np.float64)   # as in isotonic()
+    vl, vprox, tprox = g["val_labels"], g["val_prox"], g["test_prox"]
+    rv, rt = np.arange(0, len(vp), 5), np.arange(0, len(tp), 4)
+    out = {"rows_val": rv, "rows_test": rt}
+    for name, cls, kw in (("histogram_binning", orc.NetcalHistogramBinningCC, {"bins": 10}),
+                          ("isotonic_regression", orc.NetcalIsotonicRegressionCC, {})):
+        plain = cls(**kw)
+        plain.fit(vp, vl)                                               # :138-143
+        out[f"{name}_val_out"], out[f"{name}_test_out"] = plain.transform(vp)[rv], plain.transform(tp)[rt]
+        bms = BinMeanShift(name, cls, bin_strategy="quantile", normalize_conf=False, proximity_bin=5, **kw)
+        b_val = bms.fit_transform(vp, vprox, vl)                        # :126-131
+        b_test = bms.transform(tp, tprox)
+        out[f"bms_{name}_edges"] = np.asarray(bms.bin_edges, dtype=np.float64)
+        out[f"bms_{name}_val_out"], out[f"bms_{name}_test_out"] = b_val[rv], b_test[rt]
+        print("netcal_binning %s: plain test row sums %.6f..%.6f, BinMeanShift NaN rows %d" % (
+            name, np.nanmin(plain.transform(tp).sum(1)), np.nanmax(plain.transform(tp).sum(1)),
+            int(np.isnan(b_test).any(axis=1).sum())))
+    np.savez_compressed(os.path.join(OUT, "netcal_binning.npz"), **out)
+
+
 def in21k_fit(fit_classes=256, seed=0):
     """DAC fit at BASELINE.json configs[4]'s own shape - 21,841 test classes x 10,000 base classes x 768-d - on a
     class subset (the reference loop costs ~25 ms per class here): the reference's class_confidence and the
@@ -306,10 +334,15 @@ def dac_float16():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1:                      # python oracle/make_golden.py netcal_binning [...]: only those fixtures
+        for fn in sys.argv[1:]:
+            globals()[fn]()
+        sys.exit(0)
     metric_edge_cases()
     proximity_and_piece()
     density_ratio()
     isotonic()
+    netcal_binning()
     run_case("eurosat")
     run_case("sun397_l14", ks=(1, 5, 10))
     run_case("imagenet")

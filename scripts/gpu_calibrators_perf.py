@@ -48,6 +48,34 @@ for n in (2_000_000, 20_000_000):
     print("isotonic_transform", json.dumps({"n": n, "ms": ms, "GBs": 16.0 * n / ms / 1e6}), flush=True)
     del x, y
 
+for n in (2_000_000, 20_000_000):
+    x = d64(n)
+    v = torch.randint(0, 2, (n,), device="cuda", dtype=torch.uint8)
+    ms = timeit(lambda: native.sort_pairs_f64_u8(x, v), reps=3, warm=1)
+    print("sort_pairs_f64_u8", json.dumps({"n": n, "ms": ms, "Mkeys_s": n / ms / 1e3}), flush=True)
+    f = torch.randint(0, 2, (n,), device="cuda", dtype=torch.int32)
+    ms = timeit(lambda: native.prefix_sum_i32(f))
+    print("prefix_sum_i32", json.dumps({"n": n, "ms": ms, "GBs": 12.0 * n / ms / 1e6}), flush=True)
+    del x, v, f
+
+from clip_calibration_b200.trainers.calibration.netcal_binning import HistogramBinning, IsotonicRegression
+for n, c in ((50_000, 1000), (2_000_000, 100)):
+    probs = torch.softmax(torch.randn(n, c, device="cuda") * 3, dim=1)
+    labels = torch.randint(0, c, (n,), device="cuda")
+    edges = torch.linspace(0, 1, 11, dtype=torch.float64, device="cuda")
+    ms = timeit(lambda: native.ova_hist_fit(probs, labels, edges))
+    print("ova_hist_fit", json.dumps({"n": n, "c": c, "ms": ms, "GBs": 4.0 * n * c / ms / 1e6}), flush=True)
+    hb = HistogramBinning(bins=10).fit_device(probs, labels)
+    ms = timeit(lambda: hb.transform_device(probs))
+    print("ova_apply_hist", json.dumps({"n": n, "c": c, "ms": ms, "GBs": 12.0 * n * c / ms / 1e6}), flush=True)
+    if c <= 100:
+        import time
+        t0 = time.perf_counter(); iso = IsotonicRegression().fit_device(probs, labels); torch.cuda.synchronize()
+        print("ova_isotonic_fit", json.dumps({"n": n, "c": c, "s": time.perf_counter() - t0}), flush=True)
+        ms = timeit(lambda: iso.transform_device(probs))
+        print("ova_apply_isotonic", json.dumps({"n": n, "c": c, "ms": ms, "GBs": 12.0 * n * c / ms / 1e6}), flush=True)
+    del probs
+
 n = 64_000_000
 for c in (10, 1000, 49408):
     pred = torch.randint(0, c, (n,), device="cuda", dtype=torch.int32); gt = torch.randint(0, c, (n,), device="cuda")

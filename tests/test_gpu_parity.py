@@ -702,8 +702,9 @@ def test_vl_calibration_scaling_based_with_proximity(cuda_lib, golden):
     out = cal.predict(test_logits, g["test_prox"])
     assert out.dtype == np.float64
     np.testing.assert_allclose(out, g["f32_probs_out"], rtol=5e-5, atol=1e-12)   # probabilities re-derived through log/softmax in fp32
-    with pytest.raises(NotImplementedError):
-        vl_calibrator.VLCalibration(None, base_calibration_mode="bin_based", val_dict=val_dict).fit()   # netcal default
+    nameless = vl_calibrator.VLCalibration(None, base_calibration_mode="bin_based", val_dict=val_dict)
+    nameless.fit()                               # no calibrator name: the reference's if/elif chain builds nothing
+    assert nameless.base_calibrator is None
 
 
 # ----------------------------------------------------------------------------- macro-F1 (evaluator)
@@ -858,7 +859,7 @@ def test_bin_mean_shift_matches_reference_fixture(cuda_lib, golden):
         np.testing.assert_allclose(bms.transform(tp, d["test_prox"])[g["rows_test"]], g[f"bms_{strategy}_test_out"],
                                    rtol=1e-8, atol=1e-12)
     with pytest.raises(NotImplementedError):
-        BinMeanShift("histogram_binning", MultiIsotonicRegression)
+        BinMeanShift("multi_isotonic_regression", MultiIsotonicRegression, bin_strategy="kmeans")
 
 
 def test_vl_calibration_bin_based_multi_isotonic(cuda_lib, golden):
@@ -880,9 +881,123 @@ def test_vl_calibration_bin_based_multi_isotonic(cuda_lib, golden):
         # except where a point crosses a step of the fitted function
         diff = np.abs(out[g["rows_test"]] - g[key])
         assert np.quantile(diff, 0.99) < 1e-4 and diff.mean() < 1e-4
+    # a name outside the reference's if/elif chain builds nothing there either (vl_calibrator.py:121-148)
+    none = vl_calibrator.VLCalibration(None, base_calibration_mode="bin_based", base_bin_calibrator_name="platt",
+                                       val_dict=val_dict)
+    none.fit()
+    assert none.base_calibrator is None
+
+
+def test_device_sort_and_prefix_sum(cuda_lib):
+    """csrc/sort_scan.cuh (the library's own radix sort / scan, which the isotonic fit runs on): stable order of
+    (float64 key, uint8 payload) pairs incl. negative keys, +-0, infinities, heavy duplicates and sizes around the
+    2048-key tile; int32 prefix sums around the 4096-element tile, inclusive / exclusive / in place."""
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 31, 2047, 2048, 2049, 4097, 100_003, 1_500_000):
+        kinds = [rng.random(n), rng.standard_normal(n) * 10.0 ** rng.integers(-300, 300, n),
+                 rng.integers(0, 7, n).astype(np.float64) / 7.0, np.full(n, 0.25)]
+        special = rng.standard_normal(n)
+        special[rng.integers(0, n, max(1, n // 50))] = 0.0
+        special[rng.integers(0, n, max(1, n // 50))] = -0.0
+        special[rng.integers(0, n, max(1, n // 100))] = np.inf
+        special[rng.integers(0, n, max(1, n // 100))] = -np.inf
+        kinds.append(special)
+        for keys in kinds:
+            vals = rng.integers(0, 256, n).astype(np.uint8)
+            ko, vo = native.sort_pairs_f64_u8(torch.from_numpy(keys).cuda(), torch.from_numpy(vals).cuda())
+            # reference order: by the key's total order (-0.0 before +0.0), ties by input position
+            order = np.lexsort((np.arange(n), np.signbit(keys) == 0, keys))
+            assert np.array_equal(ko.cpu().numpy().view(np.uint64), keys[order].view(np.uint64))
+            assert np.array_equal(vo.cpu().numpy(), vals[order])
+    for n in (1, 255, 4095, 4096, 4097, 1_000_001):
+        x = rng.integers(0, 3, n).astype(np.int32)
+        xd = torch.from_numpy(x).cuda()
+        assert np.array_equal(native.prefix_sum_i32(xd, True).cpu().numpy(), np.cumsum(x, dtype=np.int64).astype(np.int32))
+        assert np.array_equal(native.prefix_sum_i32(xd, False).cpu().numpy(),
+                              (np.cumsum(x, dtype=np.int64) - x).astype(np.int32))
+
+
+def test_netcal_style_calibrators_match_fixture(cuda_lib, golden):
+    """HistogramBinning / IsotonicRegression (netcal's one-vs-all scheme, restated: parity with netcal itself unpinned)
+    plain (vl_calibrator.py:137-143) and under the reference's BinMeanShift (:125-131): the fixture ran the reference's
+    unmodified BinMeanShift around the oracle's statement of the two netcal classes."""
+    from clip_calibration_b200.trainers.calibration.multi_proximity_isotonic import BinMeanShift
+    from clip_calibration_b200.trainers.calibration.netcal_binning import HistogramBinning, IsotonicRegression
+    g, d = golden("netcal_binning"), golden("density_ratio")
+    vp, tp = d["val_probs"].astype(np.float64), d["test_probs"].astype(np.float64)
+    for name, cls, kw in (("histogram_binning", HistogramBinning, {"bins": 10}), ("isotonic_regression", IsotonicRegression, {})):
+        plain = cls(**kw)
+        assert plain.fit(vp, d["val_labels"]) is plain
+        np.testing.assert_allclose(plain.transform(vp)[g["rows_val"]], g[f"{name}_val_out"], rtol=1e-12, atol=1e-15)
+        test_out = plain.transform(tp)
+        assert test_out.dtype == np.float64
+        np.testing.assert_allclose(test_out[g["rows_test"]], g[f"{name}_test_out"], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(test_out.sum(1), 1.0, rtol=1e-12)
+        # float32 probabilities are widened exactly: same result as their float64 copy; torch in -> torch out
+        out32 = plain.transform(torch.from_numpy(d["test_probs"]).cuda())
+        assert out32.is_cuda and np.array_equal(out32.cpu().numpy(), test_out)
+        bms = BinMeanShift(name, cls, bin_strategy="quantile", normalize_conf=False, proximity_bin=5, **kw)
+        val_out = bms.fit_transform(vp, d["val_prox"], d["val_labels"])
+        np.testing.assert_allclose(bms.bin_edges, g[f"bms_{name}_edges"], rtol=1e-7)
+        # BinMeanShift exp-normalises its input for these two methods (reference :219-220): inputs move by an ulp,
+        # the bin maps / knots with them
+        np.testing.assert_allclose(val_out[g["rows_val"]], g[f"bms_{name}_val_out"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(bms.transform(tp, d["test_prox"])[g["rows_test"]], g[f"bms_{name}_test_out"],
+                                   rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,c,seed", [(4000, 37, 0), (20_000, 101, 1), (513, 3, 2)])
+def test_netcal_style_calibrators_against_the_oracle(cuda_lib, n, c, seed):
+    """Random softmax outputs with classes that never occur in y, confidences exactly on bin edges (0, 0.1 ... 1.0),
+    empty bins, the binary (1-D) form and independent_probabilities - against oracle.cpu_oracle.Netcal*CC."""
+    from clip_calibration_b200.trainers.calibration.netcal_binning import HistogramBinning, IsotonicRegression
+    rng = np.random.default_rng(seed)
+    logits = rng.standard_normal((n, c)) * 3.0
+    y = rng.integers(0, c - 1, n)                               # the last class never occurs
+    logits[np.arange(n), y] += 2.0
+    p = np.exp(logits - logits.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    p[:: 97, 0] = np.linspace(0.0, 1.0, 11)[rng.integers(0, 11, len(p[:: 97]))]      # values on the bin edges
+    q = rng.random((n // 2, c))
+    q /= q.sum(1, keepdims=True)
+    for mine, ref in ((HistogramBinning(bins=15), orc.NetcalHistogramBinningCC(bins=15)),
+                      (IsotonicRegression(), orc.NetcalIsotonicRegressionCC()),
+                      (HistogramBinning(independent_probabilities=True), orc.NetcalHistogramBinningCC(independent_probabilities=True))):
+        got = mine.fit_transform(p, y)
+        want = ref.fit_transform(p, y)
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-15)
+        assert np.all(got[:, c - 1] == 0.0)
+        np.testing.assert_allclose(mine.transform(q), ref.transform(q), rtol=1e-12, atol=1e-15)
+    conf, hit = p[:, 0], (y == 0).astype(np.int64)
+    for mine, ref in ((HistogramBinning(bins=10), orc.NetcalHistogramBinningCC(bins=10)),
+                      (IsotonicRegression(), orc.NetcalIsotonicRegressionCC())):
+        got = mine.fit_transform(conf, hit)
+        assert got.shape == (n,)
+        np.testing.assert_allclose(got, ref.fit_transform(conf, hit), rtol=1e-12, atol=1e-15)
     with pytest.raises(NotImplementedError):
-        vl_calibrator.VLCalibration(None, base_calibration_mode="bin_based", base_bin_calibrator_name="histogram_binning",
-                                    val_dict=val_dict).fit()
+        HistogramBinning().fit(p[:, :2], y)
+    with pytest.raises(NotImplementedError):
+        HistogramBinning(equal_intervals=False)
+
+
+def test_vl_calibration_bin_based_netcal_names(cuda_lib, golden):
+    """VLCalibration(base_calibration_mode='bin_based') with the two netcal names, with and without proximity."""
+    g, d = golden("netcal_binning"), golden("density_ratio")
+    val_logits = np.log(d["val_probs"].astype(np.float64))
+    test_logits = np.log(d["test_probs"].astype(np.float64))
+    val_dict = {"val_logits": val_logits, "val_labels": d["val_labels"], "val_image_features": None,
+                "val_text_features": None, "val_image_knn_dists": -np.log(d["val_prox"].astype(np.float64))[:, None]}
+    for name in ("histogram_binning", "isotonic_regression"):
+        for procal, key in ((False, f"{name}_test_out"), (True, f"bms_{name}_test_out")):
+            cal = vl_calibrator.VLCalibration(None, base_calibration_mode="bin_based", base_bin_calibrator_name=name,
+                                              procal_flag=procal, val_dict=val_dict)
+            cal.fit()
+            out = cal.predict(test_logits, d["test_prox"])
+            assert out.dtype == np.float64 and out.shape == test_logits.shape
+            # probabilities re-derived through log / fp32 softmax move by ~1e-7: outputs stay close except where a
+            # point crosses a bin edge / a step of the fitted function
+            diff = np.abs(out[g["rows_test"]] - g[key])
+            assert np.quantile(diff, 0.99) < 1e-3 and diff.mean() < 1e-3, (name, procal, diff.max())
 
 
 def test_custom_clip_calibration_forward_confidence(cuda_lib, golden, synth_case):

@@ -110,6 +110,31 @@ def test_isotonic_calibrators_match_reference(golden):
                                    g[f"bms_{strategy}_test_out"], rtol=1e-13, atol=1e-15)
 
 
+def test_netcal_restatement_reproduces_its_fixture(golden):
+    """The oracle's statement of netcal's one-vs-all HistogramBinning / IsotonicRegression (PARITY WITH NETCAL UNPINNED:
+    the package is not installed) against the fixture make_golden.py wrote by running the reference's unmodified
+    BinMeanShift around it; plus the properties the scheme guarantees: rows sum to 1, columns of unseen classes are 0,
+    histogram-binning outputs only take values of the fitted bin maps."""
+    g, d = golden("netcal_binning"), golden("density_ratio")
+    vp, tp = d["val_probs"].astype(np.float64), d["test_probs"].astype(np.float64)
+    for name, cls, kw in (("histogram_binning", orc.NetcalHistogramBinningCC, {"bins": 10}),
+                          ("isotonic_regression", orc.NetcalIsotonicRegressionCC, {})):
+        cal = cls(**kw).fit(vp, d["val_labels"])
+        out = cal.transform(tp)
+        np.testing.assert_allclose(out[g["rows_test"]], g[f"{name}_test_out"], rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(out.sum(1), 1.0, rtol=1e-12)
+        raw = cls(independent_probabilities=True, **kw).fit(vp, d["val_labels"]).transform(tp)
+        assert raw.min() >= 0.0 and raw.max() <= 1.0
+    y = d["val_labels"].copy()
+    y[y == 3] = 4                                              # class 3 never occurs: no sub-model, column of zeros
+    assert np.all(orc.NetcalHistogramBinningCC(bins=10).fit(vp, y).transform(tp)[:, 3] == 0.0)
+    hb = orc.NetcalHistogramBinningCC(bins=4)
+    got = hb.fit_transform(np.array([0.0, 0.1, 0.25, 0.3, 1.0]), np.array([0, 1, 1, 0, 1]))
+    # bins [0, .25) -> mean(0, 1) = .5; [.25, .5) -> mean(1, 0) = .5; [.5, .75) empty -> centre .625; [.75, 1] -> 1
+    np.testing.assert_allclose(hb.models[0][1], [0.5, 0.5, 0.625, 1.0])
+    np.testing.assert_allclose(got, [0.5, 0.5, 0.5, 0.5, 1.0])
+
+
 def test_oracle_float16_arithmetic_fit_matches_reference_golden(golden):
     """The oracle keeps the input dtype like the reference (float16 arrays stay float16 through norm / sum / exp):
     its class_confidence for float16 features equals the fixture the real reference produced (dac_float16.npz)."""
