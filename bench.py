@@ -27,6 +27,7 @@ Beyond the headline line the same JSON object carries (unless --no-extras):
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -302,6 +303,48 @@ class _StdoutToStderr:
         os.write(self._real, (line + "\n").encode())
 
 
+class StallGuard:
+    """The driver must get its line even if a multi-rank step stops making progress (a collective that never
+    completes would otherwise sit in NCCL's watchdog for minutes and end in SIGABRT with nothing printed).  Timed loops
+    arm the guard and `beat()` once per step; if no beat arrives for `limit` seconds the guard reports where it
+    stalled and which streams are busy, lets rank 0 print the line from what HAS been measured (marked "stalled"),
+    and ends the process.  Every rank runs its own guard, so all of them leave."""
+
+    def __init__(self):
+        self.deadline = None
+        self.where = ""
+        self.limit = 0.0
+        self.on_stall = None                 # set by main(): callable(where) -> None, must not return normally
+        self.context = {}
+        self._lock = threading.Lock()
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def arm(self, where: str, limit: float = 75.0):
+        with self._lock:
+            self.where, self.limit, self.deadline = where, float(limit), time.time() + float(limit)
+
+    def beat(self):
+        with self._lock:
+            if self.deadline is not None:
+                self.deadline = time.time() + self.limit
+
+    def disarm(self):
+        with self._lock:
+            self.deadline = None
+
+    def _run(self):
+        while True:
+            time.sleep(1.0)
+            with self._lock:
+                late = self.deadline is not None and time.time() > self.deadline
+                where = self.where
+            if late and self.on_stall is not None:
+                self.on_stall(where)
+
+
+GUARD = None                                 # created by main() for the CUDA arm
+
+
 class Ctx:
     """Process-wide handles of the CUDA arm."""
 
@@ -346,7 +389,7 @@ def static_traffic(w: Workload):
 
 
 def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2e: bool, want_clocks: bool,
-            shard_fit: bool = False):
+            shard_fit: bool = False, publish=None):
     """Device-resident (and optionally end-to-end) timing of one workload with `n_images` per rank."""
     from clip_calibration_b200 import native, pipeline
     from clip_calibration_b200 import table_math as tm
@@ -430,12 +473,16 @@ def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2
         host_table.copy_(table, non_blocking=True)
 
     def timed(fn, n_steps, finish=None):
+        if GUARD is not None:
+            GUARD.arm(f"{w.name} ({n_images} images/rank): timed loop of {getattr(fn, '__name__', 'step')}")
         ctx.barrier()
         if not need_flush:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(n_steps):
                 fn()
+                if GUARD is not None:
+                    GUARD.beat()
             if finish is not None:
                 finish()
             e1.record()
@@ -452,9 +499,14 @@ def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2
                     finish()
                 e1.record()
                 pairs.append((e0, e1))
+                if GUARD is not None:
+                    GUARD.beat()
             ctx.barrier()
             total = sum(a.elapsed_time(b) for a, b in pairs)
-        return ctx.max_over_ranks(total)
+        total = ctx.max_over_ranks(total)
+        if GUARD is not None:
+            GUARD.disarm()
+        return total
 
     # ---------------- device-resident number
     for _ in range(warmup):
@@ -513,6 +565,8 @@ def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2
                                                         k=w.k, logit_scale=LOGIT_SCALE, n_bins=N_BINS,
                                                         operand_dtype=torch.bfloat16, share_text=world > 1,
                                                         overlap_fit=True)
+            if GUARD is not None:
+                GUARD.context["scorers"] = (GUARD.context.get("scorers", []) + [scorer])[-3:]
             scorer.accumulate_host(host_img, host_labels, chunk_rows=chunk_rows)                 # chunked H2D + scoring
             pending.append(scorer.reduced_table_async())                                         # all-reduce + D2H, queued
 
@@ -537,11 +591,22 @@ def measure(ctx: Ctx, w: Workload, n_images: int, steps: int, warmup: int, do_e2
             e2e_step_blocking()
         e2e_steps = max(3, steps // 2)
         blocking_ms = timed(e2e_step_blocking, e2e_steps)
+        h2d = host_img.numel() * 2 + host_labels.numel() * 8 + sum(v.numel() * v.element_size() for v in host_txt.values())
+        # what is known so far, should the pipelined loop below stall (StallGuard): the blocking form IS an end-to-end number
+        res["e2e"] = {"value": n_images * world * e2e_steps / (blocking_ms * 1e-3), "unit": UNIT,
+                      "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(3 * (N_BINS + 1) * 8),
+                      "ms_per_step": blocking_ms / e2e_steps, "steps": e2e_steps, "chunk_rows": chunk_rows,
+                      "mode": "each step's table is read back before the next step is queued (the pipelined loop did not finish)"}
+        if publish is not None:
+            publish(res)
+        if GUARD is not None:
+            GUARD.arm(f"{w.name}: warm-up of the pipelined end-to-end loop")
         for _ in range(3):            # two steps in flight need more device / pinned blocks: let the allocators reach
             e2e_step_pipelined()      # their steady state (cudaMalloc / cudaHostAlloc synchronise the device)
+            if GUARD is not None:
+                GUARD.beat()
         e2e_drain()
         e2e_ms = timed(e2e_step_pipelined, e2e_steps, finish=e2e_drain)
-        h2d = host_img.numel() * 2 + host_labels.numel() * 8 + sum(v.numel() * v.element_size() for v in host_txt.values())
         res["e2e"] = {"value": n_images * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(3 * (N_BINS + 1) * 8),
                       "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "chunk_rows": chunk_rows,
@@ -637,7 +702,7 @@ def dist_check(ctx: Ctx):
 
 
 def main():
-    global CLOCK_SAMPLE_MS
+    global CLOCK_SAMPLE_MS, GUARD
     out = _StdoutToStderr()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -662,7 +727,7 @@ def main():
 
     from clip_calibration_b200 import build as _build
     _build.build()                         # no-op when libccal.so matches the sources (it normally travels pre-built)
-    from clip_calibration_b200 import _lib
+    from clip_calibration_b200 import _lib, pipeline
 
     ctx = Ctx()
     dist, world, rank = ctx.dist, ctx.world, ctx.rank
@@ -672,67 +737,108 @@ def main():
     _lib.check(lib.ccal_check_device(), "ccal_check_device")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", ctx.local_rank))
+        # a collective that cannot complete is reported by the StallGuard within ~75 s; NCCL's own watchdog is the backstop
+        dist.init_process_group("nccl", device_id=torch.device("cuda", ctx.local_rank),
+                                timeout=datetime.timedelta(seconds=240))
+    GUARD = StallGuard()
 
     peaks = load_peaks()
-    head = measure(ctx, w, w.n_images, args.steps, args.warmup, do_e2e=True, want_clocks=True)
+    state = {"head": None, "configs": {}, "strong": None, "check_dist": None, "cpu": None}
+
+    def build_line(stalled=None):
+        head = state["head"]
+        roofline = roofline_of(w, head, peaks)
+        ms_total, steps = head["ms_total"], head["steps"]
+        check = dict(head["summary"])
+        if state["check_dist"] is not None:
+            check["dist"] = state["check_dist"]
+        line = {"metric": METRIC, "value": w.n_images * world * steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": steps, "warmup": args.warmup, "ms_per_step": ms_total / steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": config_dict(w, world), "clocks": head["clocks"], "e2e": head["e2e"],
+                "gpu_launches": head["launches"], "roofline": roofline, "cpu_baseline": state["cpu"],
+                "dac_fit_ms": head["fit_ms"], "dac_fit_ms_fp32_features": head["fit_fp32_ms"],
+                "cuda_graph_step": head["graph"], "check": check, "numa": numa}
+        if state["configs"]:
+            line["configs"] = state["configs"]
+        if state["strong"] is not None:
+            line["strong"] = state["strong"]
+        if stalled is not None:
+            line["stalled"] = stalled
+        return line
+
+    def on_stall(where):
+        # runs on the guard's thread while the main thread sits in a wait that will not return
+        dev = torch.device("cuda", ctx.local_rank)
+        busy = {}
+        try:
+            busy = {"compute": not torch.cuda.current_stream(dev).query(), "side": not pipeline._side_stream(dev).query(),
+                    "copy": not pipeline._copy_stream(dev).query()}
+            for sc in GUARD.context.get("scorers", []):
+                d = getattr(sc, "_dbg", None)
+                if d:
+                    busy.setdefault("from_dac", []).append({k: ([e.query() for e in v] if isinstance(v, list) else v.query())
+                                                            for k, v in d.items()})
+        except Exception as exc:  # noqa: BLE001
+            busy["error"] = repr(exc)
+        print(f"bench[rank {rank}]: no progress for {GUARD.limit:.0f} s in {where}; busy streams: {busy}", file=sys.stderr, flush=True)
+        if rank == 0 and state["head"] is not None:
+            try:
+                out.emit(json.dumps(build_line({"where": where, "busy_streams": busy, "note":
+                                                "measurements taken before the stall are reported; the rest is missing"})))
+            except Exception as exc:  # noqa: BLE001
+                print(f"bench: could not assemble the line after the stall: {exc!r}", file=sys.stderr, flush=True)
+        os._exit(0 if state["head"] is not None else 4)
+
+    GUARD.on_stall = on_stall
+    state["head"] = None
+    head = measure(ctx, w, w.n_images, args.steps, args.warmup, do_e2e=True, want_clocks=True,
+                   publish=lambda r: state.__setitem__("head", r))
+    state["head"] = head
     extras = not args.no_extras and args.workload == "openvocab"
-    configs, strong, check_dist, dist_ok = {}, None, None, True
+    dist_ok = True
     if extras:
         torch.cuda.empty_cache()
         w5 = WORKLOADS["in21k"]
         r5 = measure(ctx, w5, w5.n_images, max(3, args.steps // 2), 3, do_e2e=True, want_clocks=False)
         roof5 = roofline_of(w5, r5, peaks)
-        configs["in21k"] = {"workload": w5.describe(), "total_images": w5.n_images * world,
-                            "value": w5.n_images * world * r5["steps"] / (r5["ms_total"] * 1e-3), "unit": UNIT,
-                            "ms_per_step": r5["ms_total"] / r5["steps"], "steps": r5["steps"], "dac_fit_ms": r5["fit_ms"],
-                            "dac_fit_ms_fp32_features": r5["fit_fp32_ms"],
-                            "e2e": r5["e2e"], "roofline": roof5, "check": r5["summary"], "gpu_launches": r5["launches"]}
+        state["configs"]["in21k"] = {
+            "workload": w5.describe(), "total_images": w5.n_images * world,
+            "value": w5.n_images * world * r5["steps"] / (r5["ms_total"] * 1e-3), "unit": UNIT,
+            "ms_per_step": r5["ms_total"] / r5["steps"], "steps": r5["steps"], "dac_fit_ms": r5["fit_ms"],
+            "dac_fit_ms_fp32_features": r5["fit_fp32_ms"],
+            "e2e": r5["e2e"], "roofline": roof5, "check": r5["summary"], "gpu_launches": r5["launches"]}
         torch.cuda.empty_cache()
         if world > 1:
             n_strong = w.n_images // world
             rs = measure(ctx, w, n_strong, args.steps, 3, do_e2e=False, want_clocks=False, shard_fit=True)
             ms_strong, ms_weak = rs["ms_total"] / rs["steps"], head["ms_total"] / head["steps"]
-            strong = {"workload": f"{w.label}: {n_strong * world} images in TOTAL ({n_strong} per rank) x {w.n_classes} classes, "
-                                  "DAC fit sharded over the ranks (classes / N each) + all-gather of the multipliers",
-                      "value": n_strong * world * rs["steps"] / (rs["ms_total"] * 1e-3), "unit": UNIT,
-                      "ms_per_step": ms_strong, "steps": rs["steps"], "dac_fit_ms": rs["fit_ms"],
-                      "efficiency_vs_1m_per_rank_step": ms_weak / (world * ms_strong),
-                      "roofline_frac": roofline_of(w, rs, peaks)["frac"], "check": rs["summary"],
-                      "sharded_fit_identical_to_plain_fit": rs["fit_identical"]}
-            check_dist, dist_ok = dist_check(ctx)
+            state["strong"] = {
+                "workload": f"{w.label}: {n_strong * world} images in TOTAL ({n_strong} per rank) x {w.n_classes} classes, "
+                            "DAC fit sharded over the ranks (classes / N each) + all-gather of the multipliers",
+                "value": n_strong * world * rs["steps"] / (rs["ms_total"] * 1e-3), "unit": UNIT,
+                "ms_per_step": ms_strong, "steps": rs["steps"], "dac_fit_ms": rs["fit_ms"],
+                "efficiency_vs_1m_per_rank_step": ms_weak / (world * ms_strong),
+                "roofline_frac": roofline_of(w, rs, peaks)["frac"], "check": rs["summary"],
+                "sharded_fit_identical_to_plain_fit": rs["fit_identical"]}
+            GUARD.arm("N ranks == 1 rank identity check", 120.0)
+            state["check_dist"], dist_ok = dist_check(ctx)
+            GUARD.disarm()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         sys.exit(0 if dist_ok else 1)
 
-    roofline = roofline_of(w, head, peaks)
     # ---------------- CPU baseline (bounded sample, this box's host cores)
-    cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         rows, fit_classes = min(4096, w.n_images), min(512, w.n_classes)
         cpu_val, stages, kind = cpu_reference_step(w, _host_sample(w, rows), rows, fit_classes, threads)
-        cpu = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": sample_text(w, rows, fit_classes, kind), "stages_s": stages}
+        state["cpu"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": kind,
+                        "sample": sample_text(w, rows, fit_classes, kind), "stages_s": stages}
 
-    ms_total, steps = head["ms_total"], head["steps"]
-    check = dict(head["summary"])
-    if check_dist is not None:
-        check["dist"] = check_dist
-    line = {"metric": METRIC, "value": w.n_images * world * steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": steps, "warmup": args.warmup, "ms_per_step": ms_total / steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": config_dict(w, world), "clocks": head["clocks"], "e2e": head["e2e"],
-            "gpu_launches": head["launches"], "roofline": roofline, "cpu_baseline": cpu, "dac_fit_ms": head["fit_ms"],
-            "dac_fit_ms_fp32_features": head["fit_fp32_ms"],
-            "cuda_graph_step": head["graph"], "check": check, "numa": numa}
-    if configs:
-        line["configs"] = configs
-    if strong is not None:
-        line["strong"] = strong
-    out.emit(json.dumps(line))
+    out.emit(json.dumps(build_line()))
     if world > 1:
         dist.destroy_process_group()
     sys.exit(0 if dist_ok else 1)

@@ -13,6 +13,8 @@ point, so the 1-GPU and the N-GPU results are bit-identical.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -65,6 +67,7 @@ def _side_stream(device: torch.device) -> torch.cuda.Stream:
 
 
 _STAGING = {}
+_PIPE_DEBUG = bool(os.environ.get("CCAL_PIPE_DEBUG"))      # development aid: keep per-stage events of from_dac(overlap_fit=True)
 
 
 def _staging(device: torch.device, rows: int, d: int, dtype, tag: str = "ring") -> dict:
@@ -203,6 +206,7 @@ class CalibratedScorer:
             names = ("current_text_features_tuned", "base_text_features_zs", "current_text_features_zs",
                      "base_text_features_tuned")
             staged, uploaded = [], False
+            dbg = {}
             if is_root:
                 for x, nm in zip((cur_tuned, base_zs, cur_zs, base_tuned), names):
                     t = x.detach() if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
@@ -235,12 +239,19 @@ class CalibratedScorer:
                     f32 = [_to_cuda_f32(t, nm) for (t, _), nm in zip(staged, names)]
                     dac.fit(f32[1], f32[2], f32[3], f32[0], k, sync_host_copy=False)
                     cc = dac.class_confidence_device
+                    if _PIPE_DEBUG:
+                        dbg["fit_end"] = torch.cuda.Event()
+                        dbg["fit_end"].record(side)
                 else:
                     cc = torch.empty(obj.txt.shape[0], dtype=torch.float32, device=obj.device)
                 if shared:
                     torch.distributed.broadcast(cc, src=src, group=group)
                 obj._fit_done = torch.cuda.Event()
                 obj._fit_done.record(side)
+            if _PIPE_DEBUG:
+                dbg["staged"] = [ev for _, ev in staged if ev is not None]
+                dbg["fit_done"] = obj._fit_done
+                obj._dbg = dbg
             obj.class_conf = cc
             obj.class_conf.record_stream(comp)
             obj.dac = dac
