@@ -725,6 +725,10 @@ def main():
         run_reference_arm(args, w, out)
         return
 
+    # more hardware work queues than the default 8, before the CUDA context exists: the evaluation loop keeps five
+    # streams busy per rank (compute, copy, fit side stream, NCCL, NCCL's own) and streams that share a queue inherit
+    # each other's blocked waits
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     from clip_calibration_b200 import build as _build
     _build.build()                         # no-op when libccal.so matches the sources (it normally travels pre-built)
     from clip_calibration_b200 import _lib, pipeline
@@ -779,6 +783,11 @@ def main():
                 if d:
                     busy.setdefault("from_dac", []).append({k: ([e.query() for e in v] if isinstance(v, list) else v.query())
                                                             for k, v in d.items()})
+            if os.environ.get("CCAL_TRACE_MARKS"):
+                import ctypes
+                buf = ctypes.create_string_buffer(8192)
+                lib.ccal_trace_marks_report(buf, 8192)
+                busy["fit_marks"] = buf.value.decode()
         except Exception as exc:  # noqa: BLE001
             busy["error"] = repr(exc)
         print(f"bench[rank {rank}]: no progress for {GUARD.limit:.0f} s in {where}; busy streams: {busy}", file=sys.stderr, flush=True)

@@ -20,6 +20,7 @@ SIGNATURES = {
     "ccal_last_error": (c_char_p, []),
     "ccal_launch_count": (c_longlong, []),
     "ccal_check_device": (c_int, []),
+    "ccal_trace_marks_report": (c_int, [c_char_p, c_int]),
     "ccal_score_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_double), c_int,
                                  c_void_p, c_void_p]),

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 
 namespace ccal {
 
@@ -23,6 +24,25 @@ int fail(int code, const char* fmt, ...) {
 
 static std::atomic<long long> g_kernel_launches{0};
 void note_launch(int n) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+struct TraceMark { cudaEvent_t ev; int id; long long seq; unsigned long long stream; };
+constexpr int kTraceMarks = 256;
+TraceMark g_marks[kTraceMarks];
+std::atomic<long long> g_mark_seq{0};
+std::mutex g_mark_mu;
+}  // namespace
+
+void trace_mark(cudaStream_t stream, int id) {
+  static const bool on = getenv("CCAL_TRACE_MARKS") != nullptr;
+  if (!on) return;
+  std::lock_guard<std::mutex> lock(g_mark_mu);
+  const long long seq = g_mark_seq.fetch_add(1);
+  TraceMark& m = g_marks[seq % kTraceMarks];
+  if (m.ev == nullptr && cudaEventCreateWithFlags(&m.ev, cudaEventDisableTiming) != cudaSuccess) { m.ev = nullptr; return; }
+  m.id = id; m.seq = seq; m.stream = (unsigned long long)(uintptr_t)stream;
+  cudaEventRecord(m.ev, stream);
+}
 
 int num_sms() {
   static thread_local int cached_dev = -1, cached = 0;
@@ -46,6 +66,23 @@ float ceil_to_f32(double t) {
 }  // namespace ccal
 
 extern "C" int ccal_version(void) { return CCAL_VERSION; }
+
+extern "C" int ccal_trace_marks_report(char* buf, int cap) {
+  if (buf == nullptr || cap <= 0) return 0;
+  std::lock_guard<std::mutex> lock(ccal::g_mark_mu);
+  const long long end = ccal::g_mark_seq.load();
+  const long long begin = end > 96 ? end - 96 : 0;
+  int n = 0;
+  for (long long q = begin; q < end && n < cap - 48; ++q) {
+    const ccal::TraceMark& m = ccal::g_marks[q % ccal::kTraceMarks];
+    if (m.ev == nullptr || m.seq != q) continue;
+    const bool done = cudaEventQuery(m.ev) == cudaSuccess;
+    n += snprintf(buf + n, (size_t)(cap - n), "%lld:s%llx:%d%s ", q, (m.stream >> 4) & 0xfff, m.id, done ? "" : "*PENDING*");
+  }
+  cudaGetLastError();
+  buf[n < cap ? n : cap - 1] = 0;
+  return n;
+}
 
 extern "C" long long ccal_launch_count(void) { return ccal::g_kernel_launches.load(std::memory_order_relaxed); }
 

@@ -32,6 +32,9 @@ int fail(int code, const char* fmt, ...);
 
 int num_sms();
 void note_launch(int n = 1);   // process-wide count of kernels this library launched
+// Development aid (CCAL_TRACE_MARKS=1): record an event named `id` on `stream`; ccal_trace_marks_report() lists which
+// of the most recent marks the device has reached - the way to see WHERE a stream stopped making progress.
+void trace_mark(cudaStream_t stream, int id);
 
 // TMA descriptor of a [rows, d] row-major 16-bit matrix (dtype CCAL_BF16 / CCAL_F16), box =
 // {64 features, box_rows}, 128-byte swizzle, zero fill out of range (defined in score_fused.cu).

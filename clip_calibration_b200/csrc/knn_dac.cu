@@ -706,12 +706,15 @@ int launch_knn_exact(const float* ref, const float* query, int64_t nr, int64_t n
     CCAL_CUDA_OK(ws.alloc(cells * (sizeof(float) + sizeof(int)), stream));
     float* part_d = reinterpret_cast<float*>(ws.ptr);
     int* part_i = reinterpret_cast<int*>(ws.ptr + cells * sizeof(float));
+    trace_mark(stream, 30);
     knn_redo_scan_kernel<<<dim3((unsigned)parts, 16), kRedoThreads, (size_t)d * sizeof(float), stream>>>(
         ref, query, (long long)nr, d, cap, qlist, qcount, part_d, part_i);
     note_launch();
+    trace_mark(stream, 31);
     knn_redo_merge_kernel<<<kRedoSmallMax, 32, 0, stream>>>(part_d, part_i, parts, cap, k, drop_first, dist_out, idx_out,
                                                             qlist, qcount);
     note_launch();
+    trace_mark(stream, 32);
   }
   long long grid = (nq + kTile - 1) / kTile;
   const long long cap = (long long)num_sms() * 4;
@@ -720,6 +723,7 @@ int launch_knn_exact(const float* ref, const float* query, int64_t nr, int64_t n
   knn_l2_kernel<<<(int)grid, 256, 0, stream>>>(ref, query, (long long)nr, (long long)nq, d, k, drop_first,
                                                dist_out, idx_out, qlist, qcount);
   note_launch();
+  trace_mark(stream, 33);
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
 }
@@ -764,11 +768,18 @@ extern "C" int ccal_knn_l2_exhaustive(const float* ref, const float* query, int6
 }
 
 // One library-owned non-blocking stream per device for the second kNN chain of ccal_dac_fit (created on first use,
-// never destroyed; CCAL_DAC_ONE_STREAM=1 keeps everything on the caller's stream).
+// never destroyed).  OPT-IN (CCAL_DAC_TWO_STREAMS=1): it buys 0.09 ms per large fit on an otherwise idle GPU, but a
+// stream the caller does not know about is one more stream sharing the device's hardware queues.  Measured on 2 x
+// B200 (round 2, profiles/r02i_stall_trace.txt): in a pipelined evaluation loop - copy stream blocked on staging
+// buffers that wait for the scoring kernels that wait for THIS fit - the second chain stopped between its
+// split_rows launch and its filter kernel in 3 of 26 processes and never resumed (the chain on the caller's stream
+// had finished): work of the extra stream queued behind another stream's blocked wait.  With one stream the fit is
+// ordered purely by the caller's stream, which 40+ multi-GPU runs never stalled on.
 static cudaStream_t fit_side_stream() {
   static std::mutex mu;
   static cudaStream_t streams[64] = {};
-  if (getenv("CCAL_DAC_ONE_STREAM")) return nullptr;
+  const char* two = getenv("CCAL_DAC_TWO_STREAMS");
+  if (two == nullptr || two[0] == '0' || getenv("CCAL_DAC_ONE_STREAM")) return nullptr;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   std::lock_guard<std::mutex> lock(mu);
@@ -795,21 +806,26 @@ extern "C" int ccal_dac_fit(const float* base_zs, const float* cur_zs, const flo
     return launch_dac_fit_small(base_zs, cur_zs, base_tuned, cur_tuned, b, c, d, k, class_conf_out, knn_idx_zs_out,
                                 knn_idx_tuned_out, knn_dist_zs_out, knn_dist_tuned_out, stream);
   // The two kNN problems (zero-shot space, tuned space) are independent chains of ~9 launches each, several of them
-  // short or narrow (operand scan, split, verify, the redo of a handful of rows): they run on two streams - the
-  // caller's and a library-owned one, forked and joined by events - so that one chain's narrow kernels run underneath
-  // the other's tensor-core filter.  Still one asynchronous unit of work on the caller's stream.
+  // short or narrow (operand scan, split, verify, the redo of a handful of rows).  With CCAL_DAC_TWO_STREAMS=1 they run
+  // on two streams - the caller's and a library-owned one, forked and joined by events - so that one chain's narrow
+  // kernels run underneath the other's tensor-core filter (see fit_side_stream for why that is not the default).
   cudaStream_t side = fit_side_stream();
   int rc;
   if (side != nullptr) {
     cudaEvent_t fork, join;
     CCAL_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
     CCAL_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    trace_mark(stream, 1);
     CCAL_CUDA_OK(cudaEventRecord(fork, stream));
     CCAL_CUDA_OK(cudaStreamWaitEvent(side, fork, 0));
+    trace_mark(side, 2);
     rc = launch_knn(base_tuned, cur_tuned, b, c, d, k, 0, knn_dist_tuned_out, knn_idx_tuned_out, side);
+    trace_mark(side, 3);
     int rc2 = launch_knn(base_zs, cur_zs, b, c, d, k, 0, knn_dist_zs_out, knn_idx_zs_out, stream);
+    trace_mark(stream, 4);
     cudaEventRecord(join, side);                    // joined even on failure: the side stream must not outlive the call
     cudaStreamWaitEvent(stream, join, 0);
+    trace_mark(stream, 5);
     cudaEventDestroy(fork);
     cudaEventDestroy(join);
     if (rc) return rc;
@@ -823,6 +839,7 @@ extern "C" int ccal_dac_fit(const float* base_zs, const float* cur_zs, const flo
   const int kk = k < b ? k : b;
   dac_map_kernel<<<(c + 127) / 128, 128, 0, stream>>>(knn_dist_zs_out, knn_dist_tuned_out, c, k, kk, class_conf_out);
   note_launch();
+  trace_mark(stream, 6);
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
 }

@@ -524,6 +524,7 @@ static int run_tc(const float* ref, const float* query, int64_t nr, int64_t nq, 
   const int dp = d + kTcBlockK;                      // operand rows carry one extra 64-feature block (see split_rows_kernel)
   split_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(query, nq, d, qhi, qlo, qhn, nullptr, 0, flags);
   note_launch();
+  trace_mark(stream, 20);
   // CTA pairs when every pair gets at least one 256-row tile on most SMs; single CTAs for small query sets
   const int sms = num_sms();
   const int ctas = (nq >= (int64_t)kTcBlockM * 2 * (sms / 4)) ? 2 : 1;
@@ -569,10 +570,12 @@ static int run_tc(const float* ref, const float* query, int64_t nr, int64_t nq, 
     CCAL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mqh, mql, mrh, mrl, p));
   }
   note_launch();
+  trace_mark(stream, 21);
   CCAL_CUDA_OK(cudaGetLastError());
   knn_verify_kernel<KP><<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(ref, query, nr, nq, d, k, drop_first, plan.slots, cand, cand_score, qhn,
                                                                       rmax, dist_out, idx_out, redo_list, redo_count);
   note_launch();
+  trace_mark(stream, 22);
   CCAL_CUDA_OK(cudaGetLastError());
   return launch_knn_exact(ref, query, nr, nq, d, k, drop_first, dist_out, idx_out, redo_list, redo_count, stream);
 }
@@ -605,7 +608,9 @@ int knn_l2_tensor(const float* ref, const float* query, int64_t nr, int64_t nq, 
   float* rhn = (float*)(ws + o_rhn);
   unsigned int* rmax = (unsigned int*)(ws + o_rmax);
   unsigned int* flags = rmax + 4;
+  trace_mark(stream, 10);                          // the workspace allocation is ordered before this mark
   cudaMemsetAsync(rmax, 0, 8 * sizeof(unsigned int), stream);
+  trace_mark(stream, 11);
   // operand mode: are both matrices exactly representable in bf16 / fp16?  (one read pass, HBM-bound)
   {
     const int sms = num_sms();
@@ -615,8 +620,10 @@ int knn_l2_tensor(const float* ref, const float* query, int64_t nr, int64_t nq, 
     exact16_scan_kernel<<<(int)(g < 8 * sms ? (g < 1 ? 1 : g) : 8 * sms), 256, 0, stream>>>(query, (long long)nq * d, flags);
     note_launch(2);
   }
+  trace_mark(stream, 12);
   split_rows_kernel<<<(unsigned)((nr + 7) / 8), 256, 0, stream>>>(ref, nr, d, rhi, rlo, rhn, rmax, 1, flags);
   note_launch();
+  trace_mark(stream, 13);
   int rc = CCAL_OK;
   for (int64_t q0 = 0; q0 < nq && rc == CCAL_OK; q0 += chunk) {
     const int64_t m = (nq - q0) < chunk ? (nq - q0) : chunk;

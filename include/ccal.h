@@ -61,6 +61,11 @@ CCAL_API const char* ccal_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (monotonic). */
 CCAL_API long long ccal_launch_count(void);
 
+/* Development aid: with CCAL_TRACE_MARKS=1 in the environment the DAC-fit launch chain records named events on its
+ * streams; this writes "seq:stream:id[*PENDING*]" for the most recent ones into buf (NUL-terminated) and returns the
+ * length - the marks the device has not reached yet show where a stream stopped.  Empty without the variable. */
+CCAL_API int ccal_trace_marks_report(char* buf, int cap);
+
 /* 0 if the current device can run this library (compute capability 10.x). */
 CCAL_API int ccal_check_device(void);
 
