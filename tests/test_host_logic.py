@@ -344,3 +344,27 @@ def test_pooling_in_rounds_is_the_isotonic_fit(n, ties, seed):
     iso = IsotonicRegression(out_of_bounds="clip").fit(x, y)
     np.testing.assert_allclose(fitted, iso.predict(xs[flag]), rtol=1e-13, atol=1e-16)
     assert rounds <= 64
+
+
+def test_bench_stall_guard_fires_only_without_beats():
+    """bench.StallGuard: a timed loop that beats keeps the guard quiet; once the beats stop the callback runs with
+    the place that was armed (in bench.py it prints the line from what has been measured and ends the process)."""
+    import sys
+    import time
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench
+    fired = []
+    guard = bench.StallGuard()
+    guard.on_stall = lambda where: (fired.append(where), guard.disarm())
+    guard.arm("loop A", 1.5)
+    for _ in range(6):
+        time.sleep(0.5)
+        guard.beat()
+    assert fired == []
+    guard.disarm()
+    time.sleep(2.5)
+    assert fired == []                       # disarmed: silence is fine
+    guard.arm("loop B", 1.0)
+    time.sleep(3.5)
+    assert fired == ["loop B"]
