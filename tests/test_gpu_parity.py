@@ -1115,3 +1115,24 @@ def test_guess_pipeline_predicate_matches_the_library(cuda_lib, monkeypatch):
         assert rows in (0, n)
     monkeypatch.delenv("CCAL_SCORE_FP8", raising=False)
     assert not native.guess_pipeline_applies(10 ** 6, 49408, 512, torch.float32)
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_from_dac_resolves_the_operand_dtype_from_the_callers_features(cuda_lib, overlap):
+    """from_dac without operand_dtype: 16-bit text features are scored as they are (the root widens its device copy to
+    fp32 for the DAC fit - inferring the operand dtype from THAT copy would give fp32 on the root and 16 bits on the
+    ranks that only allocate the broadcast buffer), fp32 features take the split-precision mode; same labels either way."""
+    case = synth.make_case("dtype", 3000, 640, 320, 512, 5, 0.3, seed=3, rounding=synth.round_to_fp16)
+    img16 = torch.from_numpy(case.img).cuda().to(torch.float16)
+    labels = torch.from_numpy(case.labels).cuda()
+    preds = {}
+    for name, cast in (("fp16", lambda a: torch.from_numpy(a).to(torch.float16)), ("fp32", torch.from_numpy)):
+        scorer = pipeline.CalibratedScorer.from_dac(cast(case.base_zs), cast(case.txt_zs), cast(case.base_tuned),
+                                                    cast(case.txt_tuned), k=5, logit_scale=100.0, group=False,
+                                                    overlap_fit=overlap)
+        want = torch.float16 if name == "fp16" else torch.float32
+        assert scorer.operand_dtype == want and scorer.txt.dtype == want
+        p, _ = scorer.score(img16 if name == "fp16" else img16.float(), labels)
+        preds[name] = p.cpu()
+    # the features ARE fp16 values, so both modes see the same operands; labels may differ only on near-ties
+    assert (preds["fp16"] == preds["fp32"]).float().mean() > 0.999
