@@ -725,10 +725,6 @@ def main():
         run_reference_arm(args, w, out)
         return
 
-    # more hardware work queues than the default 8, before the CUDA context exists: the evaluation loop keeps five
-    # streams busy per rank (compute, copy, fit side stream, NCCL, NCCL's own) and streams that share a queue inherit
-    # each other's blocked waits
-    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     from clip_calibration_b200 import build as _build
     _build.build()                         # no-op when libccal.so matches the sources (it normally travels pre-built)
     from clip_calibration_b200 import _lib, pipeline
