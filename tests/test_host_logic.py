@@ -115,6 +115,24 @@ def test_no_gpu_means_loud_failure():
     with pytest.raises((RuntimeError, AssertionError)):
         DensityRatioCalibration().fit(np.full((4, 3), 1 / 3, np.float32), np.array([0, 1, 2, 0]), np.array([0, 1, 1, 0]),
                                       np.array([0.3, 0.31, 0.32, 0.33], np.float32))
+    # the new entry points of round 2: device primitives of the isotonic fit and the one-vs-all calibrators
+    with pytest.raises(_lib.CcalError):
+        native.sort_pairs_f64_u8(torch.zeros(3, dtype=torch.float64), torch.zeros(3, dtype=torch.uint8))
+    with pytest.raises(_lib.CcalError):
+        native.prefix_sum_i32(torch.zeros(3, dtype=torch.int32))
+    with pytest.raises(_lib.CcalError):
+        native.ova_hist_fit(torch.full((4, 3), 1 / 3), torch.zeros(4, dtype=torch.int64), torch.linspace(0, 1, 11, dtype=torch.float64))
+    with pytest.raises(_lib.CcalError):
+        native.ova_apply(torch.full((4, 3), 1 / 3), edges=torch.linspace(0, 1, 11, dtype=torch.float64),
+                         bin_map=torch.zeros((3, 10), dtype=torch.float64))
+    from clip_calibration_b200.trainers.calibration.netcal_binning import HistogramBinning, IsotonicRegression
+    for cal in (HistogramBinning(bins=10), IsotonicRegression()):
+        with pytest.raises((RuntimeError, AssertionError)):
+            cal.fit(np.full((4, 3), 1 / 3), np.array([0, 1, 2, 0]))
+    with pytest.raises(NotImplementedError):
+        HistogramBinning(detection=True)
+    with pytest.raises(NotImplementedError):
+        HistogramBinning(equal_intervals=False)
 
 
 def test_product_code_never_imports_the_oracle():
