@@ -49,8 +49,17 @@ def test_install_and_revert_shims(tmp_path):
                      "assert callable(p.get_knn_dists) and callable(p.get_val_image_knn_dists)\n"
                      "print(m.__file__)")
     assert out.strip().startswith(tree)
+    assert not os.path.exists(os.path.join(tree, "netcal"))          # the netcal stand-in is opt-in
+    files = install_shims.install(tree, with_netcal=True)
+    assert "netcal/binning.py" in files
+    out = _run(tree, "from netcal.binning import HistogramBinning, IsotonicRegression\n"
+                     "import clip_calibration_b200.trainers.calibration.netcal_binning as nb\n"
+                     "assert HistogramBinning is nb.HistogramBinning and IsotonicRegression is nb.IsotonicRegression\n"
+                     "print(HistogramBinning(bins=10).bins)")
+    assert out.strip() == "10"
+    install_shims.revert(tree)
+    assert not os.path.exists(os.path.join(tree, "netcal"))
     if had_reference:
-        install_shims.revert(tree)
         with open(os.path.join(tree, "tools", "metrics.py")) as fh:
             assert "KBinsDiscretizer" in fh.read()           # the reference's own file is back
 
