@@ -260,7 +260,9 @@ ova_hist_fit_kernel(const T* __restrict__ p, long long n, int c, const long long
     const long long lab = labels[row] - c0;
     for (int j = lane; j < cw; j += 32) {
       const int b = ova_bin((double)x[j], s_edges, n_bins);
-      atomicAdd(&s_cnt[j * n_bins + b], 1u);
+      // softmax tails put nearly every (row, class) pair into bin 0: that bin is not counted here but derived as
+      // n - (all other bins) by ova_hist_finish_kernel, which leaves a few per cent of the shared-memory atomics
+      if (b > 0) atomicAdd(&s_cnt[j * n_bins + b], 1u);
       if (j == lab) atomicAdd(&s_hit[j * n_bins + b], 1u);
     }
   }
@@ -269,6 +271,15 @@ ova_hist_fit_kernel(const T* __restrict__ p, long long n, int c, const long long
     if (s_cnt[j]) atomicAdd(&count[(long long)c0 * n_bins + j], s_cnt[j]);
     if (s_hit[j]) atomicAdd(&hits[(long long)c0 * n_bins + j], s_hit[j]);
   }
+}
+
+// count[j][0] = n - sum_{b >= 1} count[j][b]: every row falls into exactly one bin of every class
+__global__ void ova_hist_finish_kernel(unsigned* __restrict__ count, int c, int n_bins, unsigned n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= c) return;
+  unsigned rest = 0;
+  for (int b = 1; b < n_bins; ++b) rest += count[(long long)j * n_bins + b];
+  count[(long long)j * n_bins] = n - rest;
 }
 
 // kMode 0: histogram binning (out = bin_map[class][bin]); 1: isotonic (out = f_class(x), knots of class j are
@@ -489,7 +500,7 @@ extern "C" int ccal_ova_hist_fit(const float* p_f32, const double* p_f64, int64_
                                  const double* edges, int n_bins, uint32_t* count, uint32_t* hits, ccal_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   CCAL_REQUIRE((p_f32 != nullptr) != (p_f64 != nullptr), "ccal_ova_hist_fit: exactly one of p_f32 / p_f64 must be given");
-  CCAL_REQUIRE(n >= 0 && c >= 1, "ccal_ova_hist_fit: bad shape n=%lld c=%d", (long long)n, c);
+  CCAL_REQUIRE(n >= 0 && n < (1ll << 32) && c >= 1, "ccal_ova_hist_fit: bad shape n=%lld c=%d (n < 2^32: 32-bit counters)", (long long)n, c);
   CCAL_REQUIRE(n_bins >= 1 && n_bins <= kOvaMaxBins, "ccal_ova_hist_fit: n_bins must be in [1, %d] (got %d)", kOvaMaxBins, n_bins);
   CCAL_REQUIRE(edges && count && hits && (labels || n == 0), "ccal_ova_hist_fit: NULL pointer");
   CCAL_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(uint32_t) * (size_t)c * n_bins, stream));
@@ -507,7 +518,8 @@ extern "C" int ccal_ova_hist_fit(const float* p_f32, const double* p_f64, int64_
   } while (0)
   if (p_f32) CCAL_LAUNCH_OVA_FIT(float, p_f32); else CCAL_LAUNCH_OVA_FIT(double, p_f64);
 #undef CCAL_LAUNCH_OVA_FIT
-  note_launch();
+  ova_hist_finish_kernel<<<(c + 255) / 256, 256, 0, stream>>>(count, c, n_bins, (unsigned)n);
+  note_launch(2);
   CCAL_CUDA_OK(cudaGetLastError());
   return CCAL_OK;
 }
