@@ -239,35 +239,48 @@ __device__ __forceinline__ int ova_bin(double x, const double* edges, int n_bins
 }
 
 // counts / hits [c_tile][n_bins] live in shared memory for a tile of classes; grid = (row groups, class tiles)
+constexpr int kOvaFitThreads = 1024;           // 32 warps = 32 rows in flight per CTA, four loads in flight per lane
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kOvaFitThreads)
 ova_hist_fit_kernel(const T* __restrict__ p, long long n, int c, const long long* __restrict__ labels,
                     const double* __restrict__ edges_g, int n_bins, int tile_c, unsigned* __restrict__ count,
                     unsigned* __restrict__ hits) {
   extern __shared__ unsigned s_ova[];               // [tile_c * n_bins] counts, then [tile_c * n_bins] hits
   __shared__ double s_edges[kOvaMaxBins + 1];
+  constexpr int kWarps = kOvaFitThreads / 32;
   const int c0 = blockIdx.y * tile_c;
   const int cw = min(tile_c, c - c0);
   const int cells = cw * n_bins;
-  for (int j = threadIdx.x; j < 2 * cells; j += 256) s_ova[j] = 0;
+  for (int j = threadIdx.x; j < 2 * cells; j += kOvaFitThreads) s_ova[j] = 0;
   if (threadIdx.x <= n_bins) s_edges[threadIdx.x] = edges_g[threadIdx.x];
   __syncthreads();
   unsigned* s_cnt = s_ova;
   unsigned* s_hit = s_ova + cells;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long row = (long long)blockIdx.x * 8 + warp; row < n; row += (long long)gridDim.x * 8) {
+  for (long long row = (long long)blockIdx.x * kWarps + warp; row < n; row += (long long)gridDim.x * kWarps) {
     const T* x = p + row * (long long)c + c0;
     const long long lab = labels[row] - c0;
-    for (int j = lane; j < cw; j += 32) {
-      const int b = ova_bin((double)x[j], s_edges, n_bins);
-      // softmax tails put nearly every (row, class) pair into bin 0: that bin is not counted here but derived as
-      // n - (all other bins) by ova_hist_finish_kernel, which leaves a few per cent of the shared-memory atomics
-      if (b > 0) atomicAdd(&s_cnt[j * n_bins + b], 1u);
-      if (j == lab) atomicAdd(&s_hit[j * n_bins + b], 1u);
+    // the walk over a row is a chain of dependent-latency loads unless several are issued before the first is used
+    for (int j0 = lane; j0 < cw; j0 += 128) {
+      T v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (j0 + 32 * u < cw) ? x[j0 + 32 * u] : T(0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + 32 * u;
+        if (j < cw) {
+          const int b = ova_bin((double)v[u], s_edges, n_bins);
+          // softmax tails put nearly every (row, class) pair into bin 0: that bin is not counted here but derived as
+          // n - (all other bins) by ova_hist_finish_kernel
+          if (b > 0) atomicAdd(&s_cnt[j * n_bins + b], 1u);
+          if (j == lab) atomicAdd(&s_hit[j * n_bins + b], 1u);
+        }
+      }
     }
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < cells; j += 256) {
+  for (int j = threadIdx.x; j < cells; j += kOvaFitThreads) {
     if (s_cnt[j]) atomicAdd(&count[(long long)c0 * n_bins + j], s_cnt[j]);
     if (s_hit[j]) atomicAdd(&hits[(long long)c0 * n_bins + j], s_hit[j]);
   }
@@ -509,12 +522,12 @@ extern "C" int ccal_ova_hist_fit(const float* p_f32, const double* p_f64, int64_
   const int tile_c = std::min(c, 20480 / n_bins);              // 2 x tile_c x n_bins counters <= 160 KB of shared memory
   const size_t smem = 2 * sizeof(unsigned) * (size_t)tile_c * n_bins;
   const int tiles = (c + tile_c - 1) / tile_c;
-  const unsigned gx = (unsigned)std::min<long long>((n + 7) / 8, std::max(1, num_sms() * 2 / tiles));
+  const unsigned gx = (unsigned)std::min<long long>((n + 31) / 32, std::max(1, num_sms() * 2 / tiles));   // two 1024-thread CTAs per SM (32 registers, <= 80 KB of counters each)
   const long long* lab = reinterpret_cast<const long long*>(labels);
 #define CCAL_LAUNCH_OVA_FIT(T, ptr)                                                                                   \
   do {                                                                                                                \
     CCAL_CUDA_OK(cudaFuncSetAttribute(ova_hist_fit_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    ova_hist_fit_kernel<T><<<dim3(gx, tiles), 256, smem, stream>>>(ptr, n, c, lab, edges, n_bins, tile_c, count, hits); \
+    ova_hist_fit_kernel<T><<<dim3(gx, tiles), kOvaFitThreads, smem, stream>>>(ptr, n, c, lab, edges, n_bins, tile_c, count, hits); \
   } while (0)
   if (p_f32) CCAL_LAUNCH_OVA_FIT(float, p_f32); else CCAL_LAUNCH_OVA_FIT(double, p_f64);
 #undef CCAL_LAUNCH_OVA_FIT
